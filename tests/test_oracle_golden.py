@@ -1,0 +1,94 @@
+"""CPU: the oracle restatements reproduce the outputs recorded from the reference itself.
+
+The golden files were written by `oracle/make_golden.py`, which executed the unmodified reference
+(`/root/reference/DynamiCrafter`) in the build container.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, rel_l2
+from oracle import ddim_oracle, unet_oracle
+from pandora_b200.synthetic import synth_inputs, synth_state_dict
+
+UNET_CASES = ["unet_small_perframe", "unet_small_t499_nofs", "unet_small_sharedimg", "unet_small_b2ish"]
+DDIM_CASES = ["ddim_s5_cfg75", "ddim_s8_cfg75_r07", "ddim_s4_eta0"]
+
+
+def unet_case_inputs(meta):
+    p = meta["params"]
+    inp = synth_inputs(1, tuple(meta["latent"]), p["context_dim"], meta["seed_x"], meta["per_frame_image"])
+    if not meta["per_frame_image"]:
+        extra = synth_inputs(1, tuple(meta["latent"]), p["context_dim"], meta["seed_x"] + 7)["context"][:, :16]
+        inp["context"] = torch.cat([inp["context"], extra], 1)
+    x = torch.cat([inp["x"], inp["c_concat"]], 1)
+    t = torch.tensor([meta["t"]], dtype=torch.long)
+    fs = None if meta["fs"] is None else torch.tensor([meta["fs"]], dtype=torch.long)
+    return x, t, inp["context"], fs
+
+
+@pytest.mark.parametrize("name", UNET_CASES)
+def test_unet_oracle_matches_reference_golden(name):
+    z, meta = load_golden(name)
+    p = meta["params"]
+    sd = synth_state_dict(unet_oracle.unet_param_shapes(p), meta["seed_w"])
+    x, t, ctx, fs = unet_case_inputs(meta)
+    assert abs(float(x.double().sum()) - meta["x_sum"]) < 1e-6 * max(1.0, abs(meta["x_sum"]))
+    w_sum = float(sum(v.double().sum() for v in sd.values()))
+    assert abs(w_sum - meta["w_sum"]) < 1e-6 * max(1.0, abs(meta["w_sum"]))
+    y = unet_oracle.unet_forward(sd, p, x, t, ctx, fs)
+    assert rel_l2(y, z["y"]) < 2e-5
+    assert rel_l2(y, z["y64"]) < 2e-5
+
+
+def test_param_inventory_full_size():
+    from pandora_b200.config import UNET_512
+    shapes = unet_oracle.unet_param_shapes(UNET_512)
+    assert len(shapes) == 1516
+    n = sum(int(np.prod(s)) for s in shapes.values())
+    assert n == 1438854980
+    assert shapes["input_blocks.1.0.temopral_conv.conv1.2.weight"] == (320, 320, 3, 1, 1)
+    assert shapes["init_attn.0.proj_in.weight"] == (512, 320, 1)
+    assert shapes["input_blocks.1.1.transformer_blocks.0.attn2.to_k_ip.weight"] == (320, 1024)
+
+
+def test_timestep_embedding_uses_bf16_table():
+    t = torch.tensor([999, 19], dtype=torch.long)
+    e = unet_oracle.timestep_embedding(t, 320)
+    half = 160
+    f32 = torch.exp(-np.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    e32 = torch.cat([torch.cos(t[:, None].float() * f32), torch.sin(t[:, None].float() * f32)], -1)
+    assert e.shape == (2, 320)
+    assert float((e - e32).abs().max()) > 0.5          # the bf16 table really matters
+
+
+@pytest.mark.parametrize("name", DDIM_CASES)
+def test_ddim_oracle_matches_reference_golden(name):
+    z, meta = load_golden(name)
+    p, dp = meta["params"], meta["dparams"]
+    buf = ddim_oracle.model_schedule(**dp)
+    tab = ddim_oracle.ddim_tables(buf, meta["S"], meta["spacing"], meta["eta"])
+    assert np.array_equal(tab["timesteps"], z["timesteps"])
+    for k in ("alphas", "alphas_prev", "sigmas"):
+        assert np.array_equal(np.array(tab[k]), z[k]), k
+    assert np.array_equal(buf["sqrt_alphas_cumprod"].float().numpy(), z["sqrt_ac"])
+    sd = synth_state_dict(unet_oracle.unet_param_shapes(p), meta["seed_w"])
+    inp = synth_inputs(1, tuple(meta["latent"]), p["context_dim"], meta["seed_x"])
+    cond = dict(c_crossattn=[inp["context"]], c_concat=[inp["c_concat"]])
+    uc = dict(c_crossattn=[inp["uc_context"]], c_concat=[inp["c_concat"]])
+    fs = torch.tensor([p["default_fs"]], dtype=torch.long)
+    fn = lambda xc, t, cc, fs_: unet_oracle.unet_forward(sd, p, xc, t, cc, fs_)
+    torch.manual_seed(meta["noise_seed"])
+    x, x0 = ddim_oracle.ddim_sample(fn, buf, inp["x"], cond, uc, meta["S"], meta["spacing"], meta["eta"],
+                                    meta["cfg_scale"], meta["guidance_rescale"], fs)
+    assert rel_l2(x, z["samples"]) < 1e-4
+    assert rel_l2(x0, z["pred_x0"]) < 1e-4
+
+
+def test_trailing_schedule_quirks():
+    buf = ddim_oracle.model_schedule()
+    ac = buf["alphas_cumprod"].float()
+    assert ac[0] == 1.0 and ac[1] == 1.0 and ac[999] == 0.0      # bf16 storage
+    ts = ddim_oracle.ddim_timesteps("uniform_trailing", 50)
+    assert ts[0] == 19 and ts[-1] == 999 and len(ts) == 50
+    assert buf["scale_arr"].shape[0] == 1400
