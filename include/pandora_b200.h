@@ -1,0 +1,198 @@
+/* pandora_b200.h — C ABI of the B200-native video-denoising hot path (libpandora_b200.so).
+ *
+ * The reference (Open-Pandora / DynamiCrafter) has no FFI: its hot path is a Python class surface
+ * (`UNetModel.forward`, `DDIMSampler.sample`) whose arithmetic dispatches to torch/cuDNN/cuBLAS and
+ * optionally xformers.  Every entry point below replaces the library kernel(s) one reference call
+ * site dispatches to; the call site is cited as file:line relative to
+ * /root/reference/DynamiCrafter/lvdm/.  The Python mirror of the reference interface
+ * (`open-pandora_b200/pandora_b200/{unet,sampler}.py`) is the only caller and binds these with ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - every pointer is DEVICE memory owned by the caller (PyTorch caching allocator), including
+ *     workspaces.  The library allocates nothing on the device.
+ *   - every call enqueues work on `stream` and returns immediately: no device sync, no host reads
+ *     of device data => CUDA-graph capturable, safe under CUDA_LAUNCH_BLOCKING=1.
+ *   - return 0 on success, negative PB_E* on error; pb_last_error() gives a thread-local message.
+ *     Nothing throws, nothing calls exit().
+ *   - activations are "rows": row-major [rows, channels] with an explicit row stride (`ld*`, in
+ *     elements), channels contiguous.  A video tensor (b, c, t, h, w) is stored as rows ordered
+ *     (b, t, y, x) — one layout end to end, so none of the reference's rearranges
+ *     (modules/networks/openaimodel3d.py:43-45,236-238,570,606; modules/attention.py:300,307,369-372,
+ *     391,406) exist here.
+ *   - dtype codes: PB_F32 = 0, PB_BF16 = 1.
+ */
+#ifndef PANDORA_B200_H_
+#define PANDORA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pb_stream_t; /* a cudaStream_t */
+
+enum { PB_F32 = 0, PB_BF16 = 1 };
+enum { PB_OK = 0, PB_EINVAL = -1, PB_ECUDA = -2, PB_EUNSUPPORTED = -3 };
+
+/* A-operand addressing of pb_gemm (implicit GEMM): how logical A[m, k] is gathered from rows. */
+enum {
+  PB_A_LINEAR = 0, /* A[m,k] = a[m*lda + k]                                   nn.Linear / 1x1 conv  */
+  PB_A_CONV3X3 = 1, /* m=(n,oy,ox), k=(ky,kx,c): zero-padded 3x3 window, stride 1|2, optional     */
+                    /* nearest x2 upsample of the input folded into the addressing               */
+  PB_A_CONVT3 = 2   /* m=(b,t,p),  k=(kt,c): zero-padded 3-tap window over frames                 */
+};
+
+/* epilogue flags of pb_gemm / pb_tc_* */
+enum {
+  PB_EPI_BIAS = 1,     /* + bias[n]                                                               */
+  PB_EPI_ROWBIAS = 2,  /* + rowbias[(m / rowbias_rows) * ld_rowbias + n]   (timestep-embedding add) */
+  PB_EPI_RESIDUAL = 4, /* + residual[m*ldr + n] (fp32)                                            */
+  PB_EPI_GEGLU = 8     /* out[m,j] = u[m,j] * gelu(u[m, j + N/2]), u = acc + bias; N_out = N/2    */
+};
+
+typedef struct pb_gemm_args {
+  const void* a;        /* activations, rows of a_dtype                                           */
+  const void* w;        /* weights [N, K] row-major, K contiguous (torch Linear layout; conv kernels
+                           repacked to k = tap*Cin + c), same dtype as a                          */
+  void* c;              /* output rows [M, N_out] of c_dtype                                      */
+  const float* bias;    /* [N] fp32 or NULL                                                       */
+  const float* rowbias; /* fp32 or NULL                                                           */
+  const float* residual;/* fp32 rows or NULL                                                      */
+  int64_t M, N, K;
+  int64_t lda, ldc, ldr, ld_rowbias;
+  int64_t rowbias_rows;
+  int32_t a_dtype, c_dtype;
+  int32_t epilogue;     /* PB_EPI_* bit set                                                       */
+  int32_t a_mode;       /* PB_A_*                                                                 */
+  /* PB_A_CONV3X3: input is n_img images of in_h x in_w pixels x cin channels (row stride lda);
+     output out_h x out_w; stride 1|2; upsample!=0 => conv runs on the nearest-x2 upsampled input */
+  int32_t cin, in_h, in_w, out_h, out_w, stride, upsample;
+  /* PB_A_CONVT3: rows ordered (b, t, p): frames = T, pixels per frame = HW                       */
+  int32_t frames, frame_rows;
+} pb_gemm_args;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+int pb_version(void);
+const char* pb_last_error(void);
+/* 1 if the running device is sm_100 (tcgen05 paths usable), 0 otherwise, <0 on error */
+int pb_device_supports_tc(void);
+
+/* ---- GEMM / implicit-GEMM convolution ---------------------------------------------------------
+ * Replaces nn.Linear (modules/attention.py:53-57,86-99,418-438,269,290,336,362), ResBlock /
+ * Downsample / Upsample nn.Conv2d 3x3 (modules/networks/openaimodel3d.py:68,96,157,182,188),
+ * the 1x1 skip conv (:190), the TemporalConvBlock nn.Conv3d (3,1,1) (:258-269) and the Conv1d k=1
+ * projections of init_attn (modules/attention.py:332-334,360), with the bias add, the
+ * `h + emb_out` add (:231), the skip / residual adds (:233,282; attention.py:243-245,310,412) and
+ * GEGLU (attention.py:421-422) fused as epilogues.
+ * pb_gemm: CUDA-core fp32-accumulate path, any shape, fp32 or bf16 operands (parity / fp32 mode).   */
+int pb_gemm(const pb_gemm_args* args, pb_stream_t stream);
+
+/* tcgen05 + TMEM + TMA path (sm_100a only): bf16 operands, fp32 accumulation in tensor memory.
+ * Requires K % 64 == 0 (per tap for the conv modes), N % 16 == 0, 16-byte aligned rows.
+ * Same argument block and semantics as pb_gemm.  Returns PB_EUNSUPPORTED for shapes it cannot take
+ * (the caller then decides; there is no silent fallback inside the library).                      */
+int pb_tc_gemm(const pb_gemm_args* args, pb_stream_t stream);
+
+/* ---- GroupNorm(32) (+SiLU) ---------------------------------------------------------------------
+ * Replaces nn.GroupNorm at basics.py:76-88, openaimodel3d.py:155,179,259-268,547 (eps 1e-5) and
+ * attention.py:265,331 (eps 1e-6) plus the following nn.SiLU.  x is rows [n_inst*rows_per_inst, C];
+ * statistics are taken per (instance, group) over rows_per_inst x C/groups elements: an instance is
+ * one frame for the 2-D blocks and all T frames of a sample for the temporal blocks.
+ * pb_groupnorm_stats writes mean/rstd [n_inst, groups] fp32 (workspace: pb_groupnorm_ws_bytes).   */
+size_t pb_groupnorm_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int64_t C);
+int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_inst,
+                       int64_t rows_per_inst, int64_t C, int32_t groups, float eps,
+                       float* mean_rstd /* [n_inst, groups, 2] */, void* ws, size_t ws_bytes,
+                       pb_stream_t stream);
+int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype,
+                       int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
+                       int32_t groups, const float* mean_rstd, const float* gamma,
+                       const float* beta, int32_t silu, pb_stream_t stream);
+
+/* ---- LayerNorm ---------------------------------------------------------------------------------
+ * Replaces nn.LayerNorm(dim) eps 1e-5 at attention.py:225-227,243-245.                            */
+int pb_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,
+                 int64_t rows, int64_t C, const float* gamma, const float* beta, float eps,
+                 pb_stream_t stream);
+
+/* ---- attention ---------------------------------------------------------------------------------
+ * out = softmax(q k^T * scale) v per (batch, head), head_dim 64.  Replaces the einsum/softmax/einsum
+ * core of CrossAttention.forward (attention.py:101-125,129-135) and xformers
+ * memory_efficient_attention (:175,187).  Batch n of an operand lives at
+ *   base + (n / bdiv) * bs_outer + (n % bdiv) * bs_inner,   row i at + i * rs,  head h at + h*64
+ * (all in elements), which covers: spatial self-attention (batch = frame), text cross-attention
+ * (K/V batch = frame / T, i.e. bdiv = T, bs_inner = 0), per-frame image cross-attention, and
+ * temporal self-attention straight out of the (b, t, p) row order (batch = (b, p), rs = HW*ld).
+ * accumulate != 0 adds into `out` (attention.py:142: out = out_text + 1.0 * out_image).           */
+typedef struct pb_attn_operand {
+  const void* ptr;
+  int64_t bdiv, bs_outer, bs_inner, rs;
+} pb_attn_operand;
+
+typedef struct pb_attn_args {
+  pb_attn_operand q, k, v;
+  void* out;
+  int64_t o_bdiv, o_bs_outer, o_bs_inner, o_rs;
+  int64_t batch, heads, n_q, n_kv;
+  float scale;
+  int32_t dtype;      /* q/k/v/out element type */
+  int32_t accumulate;
+} pb_attn_args;
+
+int pb_attention(const pb_attn_args* args, pb_stream_t stream);    /* CUDA-core path, any n_q/n_kv */
+int pb_tc_attention(const pb_attn_args* args, pb_stream_t stream); /* tcgen05 flash attention, bf16 */
+
+/* ---- small / streaming kernels ---------------------------------------------------------------- */
+/* GEGLU on materialised projections (attention.py:421-422): y[m,j] = u[m,j]*gelu(u[m,j+n_out])   */
+int pb_geglu(const void* u, int32_t u_dtype, int64_t ldu, void* y, int32_t y_dtype, int64_t ldy,
+             int64_t rows, int64_t n_out, pb_stream_t stream);
+/* y = silu(x), flat (nn.SiLU of time_embed / emb_layers, openaimodel3d.py:172,376)               */
+int pb_silu(const float* x, float* y, int64_t n, pb_stream_t stream);
+/* y[i] = a[i] + b[i]  (emb + fs_embed, openaimodel3d.py:581)                                     */
+int pb_add(const float* a, const float* b, float* y, int64_t n, pb_stream_t stream);
+/* strided row copy with dtype conversion: channel concat of skip connections
+ * (openaimodel3d.py:600) and fp32-trunk -> operand casts                                          */
+int pb_copy_rows(const void* src, int32_t s_dtype, int64_t lds, void* dst, int32_t d_dtype,
+                 int64_t ldd, int64_t rows, int64_t cols, pb_stream_t stream);
+/* sinusoidal embedding with a caller-supplied frequency table (utils_diffusion.py:8-28; the table
+ * is the bf16-evaluated one, uploaded as fp32): out[b, :half]=cos(t*f), out[b, half:]=sin(t*f)   */
+int pb_timestep_embedding(const int64_t* t, const float* freqs, float* out, int64_t batch,
+                          int64_t half, pb_stream_t stream);
+/* (b, c, t, h, w) [+ second tensor concatenated on c] -> rows (b,t,y,x) x (c1+c2)
+ * (DiffusionWrapper 'hybrid' cat, models/ddpm3d.py:1079, + rearrange openaimodel3d.py:570)       */
+int pb_video_to_rows(const void* x1, int64_t c1, const void* x2, int64_t c2, int32_t in_dtype,
+                     float* rows, int64_t ld, int64_t b, int64_t t, int64_t hw, pb_stream_t stream);
+/* rows (b,t,y,x) x c -> (b, c, t, h, w)   (openaimodel3d.py:606)                                  */
+int pb_rows_to_video(const float* rows, int64_t ld, void* out, int32_t out_dtype, int64_t b,
+                     int64_t c, int64_t t, int64_t hw, pb_stream_t stream);
+
+/* ---- CFG combine + DDIM update -----------------------------------------------------------------
+ * One fused pass for DDIMSampler.p_sample_ddim (models/samplers/ddim.py:238-288) with
+ * v-parameterisation (models/ddpm3d.py:235-247), dynamic rescale (ddim.py:273-277) and
+ * rescale_noise_cfg (models/utils_diffusion.py:147-158, unbiased std) done as a 2-pass reduction.
+ * Per-step scalars are read ON THE DEVICE from `tables` [n_steps, PB_DDIM_NCOEF] at row
+ * *step_index (a device int32 the kernel post-increments when `advance`), so the 50-step loop has
+ * no host<->device scalar traffic (the reference does 4-6 .item()-style reads per step,
+ * ddim.py:263-266,274-275).  v_uncond may be NULL (no CFG).  Tensors are flat [batch, n] fp32.    */
+enum { PB_DDIM_SQRT_AC = 0,      /* sqrt_alphas_cumprod[t]            (bf16 buffer value)           */
+       PB_DDIM_SQRT_OMAC = 1,    /* sqrt_one_minus_alphas_cumprod[t]  (bf16 buffer value)           */
+       PB_DDIM_SQRT_A_PREV = 2,  /* a_prev.sqrt()                                                   */
+       PB_DDIM_SIGMA = 3,        /* sigma_t                                                         */
+       PB_DDIM_X0_RESCALE = 4,   /* prev_scale_t / scale_t (1 when dynamic rescale is off)          */
+       PB_DDIM_DIR_COEF = 5,     /* (1 - a_prev - sigma_t**2).sqrt()                                */
+       PB_DDIM_NCOEF = 8 };
+size_t pb_ddim_ws_bytes(int64_t batch);
+int pb_ddim_cfg_step(const float* x, const float* v_cond, const float* v_uncond, const float* noise,
+                     float* x_prev, float* pred_x0, int64_t batch, int64_t n, float cfg_scale,
+                     float guidance_rescale, float temperature, const float* tables,
+                     int32_t* step_index, int32_t advance, void* ws, size_t ws_bytes,
+                     pb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANDORA_B200_H_ */

@@ -1,0 +1,301 @@
+"""ctypes binding of libpandora_b200.so (the C ABI declared in include/pandora_b200.h).
+
+PyTorch is used only for device memory and streams: every wrapper takes torch tensors, passes raw
+device pointers + strides, and launches on `torch.cuda.current_stream()`.  There is no CPU or
+PyTorch fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+F32, BF16 = 0, 1
+A_LINEAR, A_CONV3X3, A_CONVT3 = 0, 1, 2
+EPI_BIAS, EPI_ROWBIAS, EPI_RESIDUAL, EPI_GEGLU = 1, 2, 4, 8
+DDIM_SQRT_AC, DDIM_SQRT_OMAC, DDIM_SQRT_A_PREV, DDIM_SIGMA, DDIM_X0_RESCALE, DDIM_DIR_COEF = range(6)
+DDIM_NCOEF = 8
+E_UNSUPPORTED = -3
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib",
+                         "libpandora_b200.so")
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("w", C.c_void_p), ("c", C.c_void_p),
+        ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("residual", C.c_void_p),
+        ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+        ("lda", C.c_int64), ("ldc", C.c_int64), ("ldr", C.c_int64), ("ld_rowbias", C.c_int64),
+        ("rowbias_rows", C.c_int64),
+        ("a_dtype", C.c_int32), ("c_dtype", C.c_int32), ("epilogue", C.c_int32), ("a_mode", C.c_int32),
+        ("cin", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("out_h", C.c_int32),
+        ("out_w", C.c_int32), ("stride", C.c_int32), ("upsample", C.c_int32),
+        ("frames", C.c_int32), ("frame_rows", C.c_int32),
+    ]
+
+
+class AttnOperand(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("bdiv", C.c_int64), ("bs_outer", C.c_int64),
+                ("bs_inner", C.c_int64), ("rs", C.c_int64)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", AttnOperand), ("k", AttnOperand), ("v", AttnOperand), ("out", C.c_void_p),
+        ("o_bdiv", C.c_int64), ("o_bs_outer", C.c_int64), ("o_bs_inner", C.c_int64), ("o_rs", C.c_int64),
+        ("batch", C.c_int64), ("heads", C.c_int64), ("n_q", C.c_int64), ("n_kv", C.c_int64),
+        ("scale", C.c_float), ("dtype", C.c_int32), ("accumulate", C.c_int32),
+    ]
+
+
+# every symbol include/pandora_b200.h declares: name -> (restype, argtypes)
+_vp, _i64, _i32, _f, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+SYMBOLS = {
+    "pb_version": (C.c_int, []),
+    "pb_last_error": (C.c_char_p, []),
+    "pb_device_supports_tc": (C.c_int, []),
+    "pb_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "pb_tc_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "pb_groupnorm_ws_bytes": (_sz, [_i64, _i64, _i64]),
+    "pb_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _sz, _vp]),
+    "pb_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "pb_layernorm": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _f, _vp]),
+    "pb_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "pb_tc_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "pb_geglu": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "pb_silu": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "pb_add": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "pb_copy_rows": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "pb_timestep_embedding": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "pb_video_to_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i64, _i64, _i64, _vp]),
+    "pb_rows_to_video": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp]),
+    "pb_ddim_ws_bytes": (_sz, [_i64]),
+    "pb_ddim_cfg_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _vp, _vp, _i32, _vp, _sz, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once). Fails loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} not found: build it with `python -m pandora_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU / PyTorch fallback for the hot path.")
+        lib = C.CDLL(_LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {load().pb_last_error().decode()}")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t):
+    """(ptr, ld) of a 2-D row view whose last dim is contiguous."""
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), (t.shape, t.stride())
+    return t.data_ptr(), t.stride(0)
+
+
+def supports_tc():
+    return load().pb_device_supports_tc() == 1
+
+
+def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=False,
+         mode=A_LINEAR, conv=None, convt=None, tc=False, M=None, K=None):
+    """c = epilogue(gather(a) @ w.T).  a, c, residual are 2-D row views; w is [N, K] contiguous."""
+    global launches
+    g = GemmArgs()
+    g.a, g.lda = _rows(a)
+    g.w = w.data_ptr()
+    g.c, g.ldc = _rows(c)
+    g.N, g.K = w.shape[0], (w.shape[1] if K is None else K)
+    g.M = c.shape[0] if M is None else M
+    g.a_dtype, g.c_dtype = dt(a), dt(c)
+    assert w.dtype == a.dtype and w.is_contiguous()
+    epi = 0
+    if bias is not None:
+        assert bias.dtype == torch.float32
+        g.bias, epi = bias.data_ptr(), epi | EPI_BIAS
+    if rowbias is not None:
+        assert rowbias.dtype == torch.float32
+        g.rowbias, g.ld_rowbias = _rows(rowbias)
+        g.rowbias_rows, epi = rowbias_rows, epi | EPI_ROWBIAS
+    if residual is not None:
+        assert residual.dtype == torch.float32
+        g.residual, g.ldr = _rows(residual)
+        epi |= EPI_RESIDUAL
+    if geglu:
+        epi |= EPI_GEGLU
+    g.epilogue, g.a_mode = epi, mode
+    if mode == A_CONV3X3:
+        g.cin, g.in_h, g.in_w, g.out_h, g.out_w, g.stride, g.upsample = conv
+    elif mode == A_CONVT3:
+        g.cin, g.frames, g.frame_rows = convt
+    lib = load()
+    fn = lib.pb_tc_gemm if tc else lib.pb_gemm
+    rc = fn(C.byref(g), _stream())
+    if rc == E_UNSUPPORTED and tc:
+        return False
+    _check(rc, "pb_tc_gemm" if tc else "pb_gemm")
+    launches += 1
+    return True
+
+
+def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32):
+    """y = GroupNorm(x) [* SiLU]; x, y 2-D row views [n_inst*rows_per_inst, C]."""
+    global launches
+    lib = load()
+    Cc = x.shape[1]
+    ws_bytes = lib.pb_groupnorm_ws_bytes(n_inst, rows_per_inst, Cc)
+    ws = torch.empty(ws_bytes // 4 + n_inst * groups * 2, dtype=torch.float32, device=x.device)
+    stats = ws[ws_bytes // 4:]
+    xp, ldx = _rows(x)
+    yp, ldy = _rows(y)
+    st = _stream()
+    _check(lib.pb_groupnorm_stats(xp, dt(x), ldx, n_inst, rows_per_inst, Cc, groups, eps,
+                                  stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "pb_groupnorm_stats")
+    _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc, groups,
+                                  stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(silu), st),
+           "pb_groupnorm_apply")
+    launches += 3
+    return stats
+
+
+def layernorm(x, y, gamma, beta, eps=1e-5):
+    global launches
+    xp, ldx = _rows(x)
+    yp, ldy = _rows(y)
+    _check(load().pb_layernorm(xp, dt(x), ldx, yp, dt(y), ldy, x.shape[0], x.shape[1],
+                               gamma.data_ptr(), beta.data_ptr(), eps, _stream()), "pb_layernorm")
+    launches += 1
+
+
+def operand(t, bdiv, bs_outer, bs_inner, rs, offset=0):
+    o = AttnOperand()
+    o.ptr = t.data_ptr() + offset * t.element_size()
+    o.bdiv, o.bs_outer, o.bs_inner, o.rs = bdiv, bs_outer, bs_inner, rs
+    return o
+
+
+def attention(q, k, v, out, o_addr, batch, heads, n_q, n_kv, scale, dtype, accumulate=False, tc=False):
+    """q, k, v: AttnOperand; out: tensor; o_addr = (bdiv, bs_outer, bs_inner, rs)."""
+    global launches
+    a = AttnArgs()
+    a.q, a.k, a.v = q, k, v
+    a.out = out.data_ptr()
+    a.o_bdiv, a.o_bs_outer, a.o_bs_inner, a.o_rs = o_addr
+    a.batch, a.heads, a.n_q, a.n_kv = batch, heads, n_q, n_kv
+    a.scale, a.dtype, a.accumulate = scale, dtype, int(accumulate)
+    lib = load()
+    fn = lib.pb_tc_attention if tc else lib.pb_attention
+    rc = fn(C.byref(a), _stream())
+    if rc == E_UNSUPPORTED and tc:
+        return False
+    _check(rc, "pb_tc_attention" if tc else "pb_attention")
+    launches += 1
+    return True
+
+
+def geglu(u, y):
+    global launches
+    up, ldu = _rows(u)
+    yp, ldy = _rows(y)
+    _check(load().pb_geglu(up, dt(u), ldu, yp, dt(y), ldy, u.shape[0], y.shape[1], _stream()), "pb_geglu")
+    launches += 1
+
+
+def silu(x, y):
+    global launches
+    _check(load().pb_silu(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "pb_silu")
+    launches += 1
+
+
+def add(a, b, y):
+    global launches
+    _check(load().pb_add(a.data_ptr(), b.data_ptr(), y.data_ptr(), y.numel(), _stream()), "pb_add")
+    launches += 1
+
+
+def copy_rows(src, dst):
+    global launches
+    sp, lds = _rows(src)
+    dp, ldd = _rows(dst)
+    _check(load().pb_copy_rows(sp, dt(src), lds, dp, dt(dst), ldd, src.shape[0], src.shape[1], _stream()),
+           "pb_copy_rows")
+    launches += 1
+
+
+def timestep_embedding(t, freqs, out):
+    global launches
+    assert t.dtype == torch.int64 and t.is_contiguous() and freqs.dtype == torch.float32
+    _check(load().pb_timestep_embedding(t.data_ptr(), freqs.data_ptr(), out.data_ptr(), t.shape[0],
+                                        freqs.shape[0], _stream()), "pb_timestep_embedding")
+    launches += 1
+
+
+def video_to_rows(x1, x2, rows, b, t, hw):
+    global launches
+    assert x1.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.dtype == x1.dtype))
+    rp, ld = _rows(rows)
+    _check(load().pb_video_to_rows(x1.data_ptr(), x1.shape[1], _ptr(x2), 0 if x2 is None else x2.shape[1],
+                                   dt(x1), rp, ld, b, t, hw, _stream()), "pb_video_to_rows")
+    launches += 1
+
+
+def rows_to_video(rows, out, b, c, t, hw):
+    global launches
+    rp, ld = _rows(rows)
+    assert out.is_contiguous() and rows.dtype == torch.float32
+    _check(load().pb_rows_to_video(rp, ld, out.data_ptr(), dt(out), b, c, t, hw, _stream()), "pb_rows_to_video")
+    launches += 1
+
+
+def ddim_cfg_step(x, v_cond, v_uncond, noise, x_prev, pred_x0, cfg_scale, guidance_rescale, temperature,
+                  tables, step_index, advance, ws):
+    global launches
+    b = x.shape[0]
+    n = x.numel() // b
+    for t_ in (x, v_cond, noise, x_prev, pred_x0):
+        assert t_.dtype == torch.float32 and t_.is_contiguous()
+    assert v_uncond is None or (v_uncond.dtype == torch.float32 and v_uncond.is_contiguous())
+    assert tables.dtype == torch.float32 and step_index.dtype == torch.int32
+    _check(load().pb_ddim_cfg_step(x.data_ptr(), v_cond.data_ptr(), _ptr(v_uncond), noise.data_ptr(),
+                                   x_prev.data_ptr(), pred_x0.data_ptr(), b, n, cfg_scale, guidance_rescale,
+                                   temperature, tables.data_ptr(), step_index.data_ptr(), int(advance),
+                                   _ptr(ws), 0 if ws is None else ws.numel() * ws.element_size(), _stream()),
+           "pb_ddim_cfg_step")
+    launches += 2 + (2 if guidance_rescale > 0 and v_uncond is not None else 0)

@@ -1,0 +1,98 @@
+"""CPU: host-side logic of the product (no kernels run here): ABI surface, state-dict contract,
+schedule tables against the reference goldens, loud failure without CUDA."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden
+from oracle import ddim_oracle, unet_oracle
+from pandora_b200 import DDIMSampler, LatentDiffusionLite, UNetModel, abi, config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_and_binding_agree_and_library_exports_everything():
+    hdr = open(os.path.join(ROOT, "include", "pandora_b200.h")).read()
+    declared = set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", hdr)) - {"pb_stream_t"}
+    assert declared == set(abi.SYMBOLS), declared ^ set(abi.SYMBOLS)
+    if not os.path.exists(abi.lib_path()):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = abi.load()                      # resolves every symbol, no compute calls
+    assert lib.pb_version() >= 100
+
+
+def test_struct_layouts_match_header_field_order():
+    assert [f[0] for f in abi.GemmArgs._fields_][:9] == ["a", "w", "c", "bias", "rowbias", "residual", "M", "N", "K"]
+    assert abi.GemmArgs.M.offset == 48 and abi.GemmArgs.a_dtype.offset == 112
+    assert abi.AttnOperand.rs.offset == 32 and abi.AttnArgs.out.offset == 120
+
+
+@pytest.mark.parametrize("cfg", [config.small_unet(), config.UNET_512])
+def test_state_dict_contract(cfg):
+    with torch.device("meta"):
+        m = UNetModel(**cfg)
+    sd = m.state_dict()
+    shapes = unet_oracle.unet_param_shapes(cfg)
+    assert set(sd) == set(shapes)
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    assert m.out_channels == cfg["out_channels"]
+
+
+def test_unsupported_options_fail_loudly():
+    with pytest.raises(NotImplementedError, match="use_relative_position"):
+        UNetModel(**dict(config.small_unet(), use_relative_position=True))
+    with pytest.raises(NotImplementedError, match="num_head_channels"):
+        UNetModel(**dict(config.small_unet(), num_head_channels=32))
+
+
+def test_zero_init_matches_reference_constructor():
+    m = UNetModel(**config.small_unet())
+    sd = m.state_dict()
+    for k in ("out.2.weight", "input_blocks.1.0.out_layers.3.weight", "input_blocks.1.1.proj_out.weight",
+              "input_blocks.1.0.temopral_conv.conv4.3.weight", "fps_embedding.2.weight", "init_attn.0.proj_out.bias"):
+        assert float(sd[k].abs().max()) == 0.0, k
+    assert float(sd["input_blocks.1.0.in_layers.2.weight"].abs().max()) > 0
+
+
+@pytest.mark.parametrize("name", ["ddim_s5_cfg75", "ddim_s8_cfg75_r07", "ddim_s4_eta0"])
+def test_schedule_tables_match_reference_golden(name):
+    z, meta = load_golden(name)
+    model = LatentDiffusionLite(None, **meta["dparams"])
+    s = DDIMSampler(model)
+    s.make_schedule(meta["S"], meta["spacing"], meta["eta"], verbose=False)
+    assert np.array_equal(np.asarray(s.ddim_timesteps), z["timesteps"])
+    assert np.array_equal(np.asarray([float(v) for v in s.ddim_alphas]), z["alphas"])
+    assert np.array_equal(np.asarray(s.ddim_alphas_prev, dtype=np.float64), z["alphas_prev"])
+    assert np.array_equal(np.asarray([float(v) for v in s.ddim_sigmas]), z["sigmas"])
+    assert np.array_equal(model.sqrt_alphas_cumprod.float().numpy(), z["sqrt_ac"])
+    assert np.array_equal(model.sqrt_one_minus_alphas_cumprod.float().numpy(), z["sqrt_omac"])
+    tab, idx = s._step_table(False)
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    otab = ddim_oracle.ddim_tables(ddim_oracle.model_schedule(**meta["dparams"]), meta["S"], meta["spacing"], meta["eta"])
+    for i in range(meta["S"]):
+        a_prev, sig = f32(otab["alphas_prev"][i]), f32(otab["sigmas"][i])
+        assert tab[i, abi.DDIM_SQRT_A_PREV] == a_prev.sqrt()
+        assert tab[i, abi.DDIM_SIGMA] == sig
+        d = (1.0 - a_prev - sig ** 2).sqrt()
+        assert tab[i, abi.DDIM_DIR_COEF] == d or (torch.isnan(d) and torch.isnan(tab[i, abi.DDIM_DIR_COEF]))
+        assert tab[i, abi.DDIM_X0_RESCALE] == f32(otab["scale_prev"][i]) / f32(otab["scale"][i])
+        assert tab[i, abi.DDIM_SQRT_AC] == float(z["sqrt_ac"][z["timesteps"][i]])
+    assert idx.tolist() == list(range(meta["S"]))
+
+
+def test_forward_without_cuda_raises_not_falls_back():
+    m = UNetModel(**config.small_unet())
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(1, 8, 16, 8, 8), torch.zeros(1, dtype=torch.long), context=torch.zeros(1, 333, 128))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "open-pandora_b200", "pandora_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f

@@ -1,0 +1,152 @@
+"""GPU parity proper: native UNetModel / DDIMSampler (through the C ABI) against
+  (1) the golden outputs recorded from the reference itself, and
+  (2) the CPU oracle on fresh seeded inputs,
+in both precision modes.  Tolerances are BASELINE.json's: per-step rel-L2 <= 1e-3 (fp32 mode),
+<= 2e-2 (bf16 mode); final-latent PSNR >= 40 dB against the fp32 reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, psnr, rel_l2
+from test_oracle_golden import DDIM_CASES, UNET_CASES, unet_case_inputs
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL, BF16_TOL, PSNR_MIN = 1e-3, 2e-2, 40.0
+
+
+def native_unet(params, seed, dtype=torch.float32):
+    from pandora_b200 import UNetModel
+    from pandora_b200.synthetic import randomize_module_
+    m = UNetModel(**params).eval()
+    randomize_module_(m, seed)
+    return m.to(device="cuda", dtype=dtype)
+
+
+@pytest.mark.parametrize("name", UNET_CASES)
+def test_unet_fp32_matches_reference_golden(name):
+    z, meta = load_golden(name)
+    m = native_unet(meta["params"], meta["seed_w"])
+    x, t, ctx, fs = unet_case_inputs(meta)
+    y = m(x.cuda(), t.cuda(), context=ctx.cuda(), fs=None if fs is None else fs.cuda(),
+          cfg_img=None, round_info=(1, 1), gr_progress_bar=None)       # junk kwargs are swallowed
+    assert y.shape == tuple(z["y"].shape) and y.dtype == torch.float32
+    e = rel_l2(y, z["y64"])
+    print(f"{name}: fp32 mode rel-L2 vs reference fp64 = {e:.3e}")
+    assert e < FP32_TOL
+    assert e < 5e-5   # in practice the exact path sits at fp32 round-off
+
+
+@pytest.mark.parametrize("name", UNET_CASES)
+@pytest.mark.parametrize("weights", ["bf16", "fp32-forced"])
+def test_unet_bf16_matches_reference_golden(name, weights):
+    z, meta = load_golden(name)
+    if weights == "bf16":      # the way Open-Pandora runs it: model.to(bf16), x in bf16 (gradio_app.py:128-129)
+        m = native_unet(meta["params"], meta["seed_w"], torch.bfloat16)
+    else:                      # fp32 master weights, bf16 compute forced
+        m = native_unet(meta["params"], meta["seed_w"])
+        m.compute_mode = "bf16"
+    x, t, ctx, fs = unet_case_inputs(meta)
+    y = m(x.cuda(), t.cuda(), context=ctx.cuda(), fs=None if fs is None else fs.cuda())
+    e = rel_l2(y, z["y64"])
+    print(f"{name}/{weights}: bf16 mode rel-L2 vs reference fp64 = {e:.3e}")
+    assert e < BF16_TOL
+
+
+def test_unet_simt_and_tc_paths_agree_in_bf16():
+    z, meta = load_golden("unet_small_perframe")
+    m = native_unet(meta["params"], meta["seed_w"], torch.bfloat16)
+    x, t, ctx, fs = unet_case_inputs(meta)
+    args = (x.cuda(), t.cuda())
+    kw = dict(context=ctx.cuda(), fs=fs.cuda())
+    m.kernel_impl = "simt"
+    y_simt = m(*args, **kw)
+    m.kernel_impl = "auto"
+    m.invalidate_packed_weights()
+    y_tc = m(*args, **kw)
+    assert rel_l2(y_tc, y_simt) < 1e-2
+    assert rel_l2(y_tc, z["y64"]) < BF16_TOL
+
+
+def test_unet_batch2_against_oracle():
+    """b=2 with different timesteps / fs per sample, fresh inputs, oracle on CPU."""
+    from oracle import unet_oracle
+    from pandora_b200 import config
+    from pandora_b200.synthetic import synth_inputs, synth_state_dict
+    p = config.small_unet()
+    m = native_unet(p, 7)
+    sd = synth_state_dict(unet_oracle.unet_param_shapes(p), 7)
+    inp = synth_inputs(2, (4, 16, 8, 8), p["context_dim"], seed=11)
+    x = torch.cat([inp["x"], inp["c_concat"]], 1)
+    t = torch.tensor([999, 259], dtype=torch.long)
+    fs = torch.tensor([24, 10], dtype=torch.long)
+    ref = unet_oracle.unet_forward(sd, p, x, t, inp["context"], fs)
+    y = m(x.cuda(), t.cuda(), context=inp["context"].cuda(), fs=fs.cuda())
+    assert rel_l2(y, ref) < 5e-5
+    y2 = m(inp["x"].cuda(), t.cuda(), context=inp["context"].cuda(), fs=fs.cuda(), x_concat=[inp["c_concat"].cuda()])
+    assert torch.equal(y, y2)          # folded channel concat == explicit torch.cat
+    m.compute_mode = "bf16"
+    yb = m(x.cuda(), t.cuda(), context=inp["context"].cuda(), fs=fs.cuda())
+    assert rel_l2(yb, ref) < BF16_TOL
+
+
+def test_cpu_input_fails_loudly():
+    from pandora_b200 import UNetModel, config
+    m = UNetModel(**config.small_unet())
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(1, 8, 16, 8, 8), torch.zeros(1, dtype=torch.long), context=torch.zeros(1, 333, 128))
+
+
+def _sampler_run(meta, dtype, mode=None):
+    from pandora_b200 import DDIMSampler, LatentDiffusionLite
+    from pandora_b200.synthetic import synth_inputs
+    p, dp = meta["params"], meta["dparams"]
+    unet = native_unet(p, meta["seed_w"], dtype)
+    unet.compute_mode = mode
+    model = LatentDiffusionLite(unet, **dp).cuda()
+    sampler = DDIMSampler(model)
+    inp = {k: v.cuda() for k, v in synth_inputs(1, tuple(meta["latent"]), p["context_dim"], meta["seed_x"]).items()}
+    cond = dict(c_crossattn=[inp["context"]], c_concat=[inp["c_concat"]])
+    uc = dict(c_crossattn=[inp["uc_context"]], c_concat=[inp["c_concat"]])
+    fs = torch.tensor([p["default_fs"]], dtype=torch.long, device="cuda")
+    # the golden run drew its noise from the CPU generator; replay the identical draws
+    torch.manual_seed(meta["noise_seed"])
+    noises = [torch.randn((1, *meta["latent"])) for _ in range(meta["S"])]
+    it = iter(noises)
+    orig = torch.randn
+    try:
+        torch.randn = lambda *a, **k: next(it).cuda()
+        samples, inter = sampler.sample(
+            S=meta["S"], batch_size=1, shape=tuple(meta["latent"]), conditioning=cond,
+            unconditional_conditioning=uc, unconditional_guidance_scale=meta["cfg_scale"], eta=meta["eta"],
+            x_T=inp["x"], fs=fs, verbose=False, timestep_spacing=meta["spacing"],
+            guidance_rescale=meta["guidance_rescale"], cfg_img=None, round_info=(1, 1), gr_progress_bar=None,
+            unconditional_conditioning_img_nonetext=None,
+            precision=torch.bfloat16 if dtype == torch.bfloat16 else None)
+    finally:
+        torch.randn = orig
+    return sampler, samples, inter
+
+
+@pytest.mark.parametrize("name", DDIM_CASES)
+def test_sampler_fp32_matches_reference_golden(name):
+    z, meta = load_golden(name)
+    sampler, samples, inter = _sampler_run(meta, torch.float32)
+    assert np.array_equal(np.asarray(sampler.ddim_timesteps), z["timesteps"])
+    assert np.array_equal(np.asarray([float(v) for v in sampler.ddim_sigmas]), z["sigmas"])
+    e = rel_l2(samples, z["samples"])
+    print(f"{name}: fp32 final latent rel-L2 = {e:.3e}, PSNR = {psnr(samples, z['samples']):.1f} dB")
+    assert e < FP32_TOL
+    assert rel_l2(inter["pred_x0"][-1], z["pred_x0"]) < FP32_TOL
+    assert psnr(samples, z["samples"]) > 80
+
+
+@pytest.mark.parametrize("name", DDIM_CASES)
+def test_sampler_bf16_psnr_vs_fp32_reference(name):
+    z, meta = load_golden(name)
+    _, samples, _ = _sampler_run(meta, torch.bfloat16)
+    assert samples.dtype == torch.bfloat16
+    q = psnr(samples.float(), z["samples"])
+    print(f"{name}: bf16 final latent PSNR vs fp32 reference = {q:.1f} dB, rel-L2 = {rel_l2(samples.float(), z['samples']):.3e}")
+    assert q >= PSNR_MIN
