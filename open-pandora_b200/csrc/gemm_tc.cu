@@ -1,7 +1,433 @@
-// gemm_tc.cu — placeholder, replaced by the tcgen05 implementation.
-#include "common.cuh"
+// gemm_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM for the bf16 hot path (sm_100a).
+//
+//   C[m, n] = epilogue( sum_k A[m, k] * W[n, k] )      A, W bf16; fp32 accumulation in tensor memory
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      TMA producer   : cp.async.bulk.tensor tiles of A (128 rows x 64 k) and W (block_n x 64 k)
+//                                into a ring of 128B-swizzled shared-memory stages (mbarrier full/empty)
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (M=128, N=block_n, K=16) x4 per
+//                                stage; tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2..5  epilogue       : tcgen05.ld the 128 x block_n fp32 accumulator (each thread owns one row),
+//                                fuse bias / timestep-embedding row bias / residual / GEGLU, convert and store
+// The accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the
+// MMAs of tile i+1.
+//
+// The A operand is addressed purely by TMA coordinates, so convolution needs no im2col buffer:
+//   LINEAR   2-D map [M][K]
+//   CONV3X3  4-D map [n][y][x][c]; tap (ky,kx) = the same box shifted by (ky-1, kx-1); out-of-bounds
+//            rows/columns are zero-filled by the TMA unit, which IS the conv's zero padding
+//   CONVT3   4-D map [b][t][p][c]; tap kt = box shifted by kt-1 frames (zero-filled outside the clip)
+// A 128-row tile is a BW x BH x BN (x, y, image) or BP x BT (pixel, frame) brick chosen so the brick tiles
+// the tensor exactly.
+#include <string.h>
 
-extern "C" int pb_tc_gemm(const pb_gemm_args*, pb_stream_t) {
-  pb::set_error("pb_tc_gemm: not built");
-  return PB_EUNSUPPORTED;
+#include "tc_common.cuh"
+
+namespace pb {
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 220 * 1024;
+
+struct TcParams {
+  void* c;
+  const float* bias;
+  const float* rowbias;
+  const float* residual;
+  int64_t M, ldc, ldr, ldrb, rb_rows;
+  int N;                 // accumulator columns in total (weight rows)
+  int block_n;           // accumulator columns per tile
+  int n_tiles, m_tiles;
+  int k_chunks;          // Cin / 64 (per tap) or K / 64
+  int taps;              // 1, 9 or 3
+  int stages;
+  int epi;
+  int geglu_half;        // N / 2 when GEGLU
+  // brick geometry (conv modes)
+  int bw, bh, bn_img;    // CONV3X3: brick x, y, images ; CONVT3: bw = pixels, bh = frames
+  int W, H;              // CONV3X3: image size ; CONVT3: W = HW (pixels per frame), H = T
+  int tiles_x, tiles_y;  // CONV3X3: W/bw, H/bh ; CONVT3: HW/bw, T/bh
+};
+
+template <int MODE>
+__device__ __forceinline__ int64_t out_row(const TcParams& p, int m_tile, int r) {
+  if (MODE == PB_A_LINEAR) return (int64_t)m_tile * BLOCK_M + r;
+  const int tx = m_tile % p.tiles_x;
+  const int ty = (m_tile / p.tiles_x) % p.tiles_y;
+  const int tn = m_tile / (p.tiles_x * p.tiles_y);
+  const int bx = r % p.bw;
+  const int by = (r / p.bw) % p.bh;
+  const int bi = r / (p.bw * p.bh);
+  // CONV3X3: ((img*H + y)*W + x) ; CONVT3 (bn_img = 1): ((b*T + t)*HW + pix)
+  return ((int64_t)(tn * p.bn_img + bi) * p.H + (ty * p.bh + by)) * p.W + (tx * p.bw + bx);
+}
+
+template <int MODE, bool GEGLU, typename TC>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // manual 1024-byte alignment (swizzle-128B atoms)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+        int cx = 0, cy = 0, cn = 0;
+        if (MODE != PB_A_LINEAR) {
+          cx = (m_tile % p.tiles_x) * p.bw;
+          cy = ((m_tile / p.tiles_x) % p.tiles_y) * p.bh;
+          cn = (m_tile / (p.tiles_x * p.tiles_y)) * p.bn_img;
+        }
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * stage_bytes;
+          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), (uint32_t)stage_bytes);
+          if (MODE == PB_A_LINEAR) {
+            tma_load_2d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
+          } else if (MODE == PB_A_CONV3X3) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx + kx - 1, cy + ky - 1, cn);
+          } else {
+            tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
+          }
+          const int kcol = it * BLOCK_K;   // weight column = tap*Cin + kc*64
+          if (GEGLU) {
+            const int half = p.block_n >> 1;
+            tma_load_2d(b_dst, &tmB, full_bar(stage), kcol, n_tile * half);
+            tma_load_2d(b_dst + half * BLOCK_K * 2, &tmB, full_bar(stage), kcol, p.geglu_half + n_tile * half);
+          } else {
+            tma_load_2d(b_dst, &tmB, full_bar(stage), kcol, n_tile * p.block_n);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzled row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+    const int r = quarter * 32 + lane;       // accumulator row owned by this thread
+    TC* C = reinterpret_cast<TC*>(p.c);
+    int acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+      const int64_t m = out_row<MODE>(p, m_tile, r);
+      const bool row_ok = m < p.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+      const int out_cols = GEGLU ? (p.block_n >> 1) : p.block_n;
+      const int64_t n0 = (int64_t)n_tile * out_cols;       // first output column of the tile
+      const float* rb = (p.epi & PB_EPI_ROWBIAS) && row_ok ? p.rowbias + (m / p.rb_rows) * p.ldrb : nullptr;
+      const float* rs = (p.epi & PB_EPI_RESIDUAL) && row_ok ? p.residual + m * p.ldr : nullptr;
+      for (int c0 = 0; c0 < out_cols; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        float g[16];
+        if (GEGLU) tmem_ld16(t_row + (uint32_t)(out_cols + c0), g);
+        tmem_ld_wait();
+        if (p.epi & PB_EPI_BIAS) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            if (GEGLU) {
+              float4 g4 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_half + n0 + c0 + j));
+              g[j] += g4.x; g[j + 1] += g4.y; g[j + 2] += g4.z; g[j + 3] += g4.w;
+            }
+          }
+        }
+        if (GEGLU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= gelu_f(g[j]);
+        }
+        if (row_ok) {
+          if (rb) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 t4 = __ldg(reinterpret_cast<const float4*>(rb + n0 + c0 + j));
+              v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+            }
+          }
+          if (rs) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              float4 t4 = *reinterpret_cast<const float4*>(rs + n0 + c0 + j);
+              v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+            }
+          }
+          TC* dst = C + m * p.ldc + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+            store4(dst + j, o);
+          }
+        }
+      }
+      // accumulator buffer drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return PB_ECUDA;
+  }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] stride0 %llu",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+              rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+              (unsigned long long)(rank > 1 ? strides_bytes[0] : 0));
+    return PB_ECUDA;
+  }
+  return PB_OK;
+}
+
+static int largest_divisor_leq(int n, int cap) {
+  for (int d = cap < n ? cap : n; d >= 1; --d)
+    if (n % d == 0) return d;
+  return 1;
+}
+
+static int pick_block_n(int n_cols, int cap) {
+  // largest multiple of 16 that divides n_cols, <= cap
+  for (int bn = cap - cap % 16; bn >= 16; bn -= 16)
+    if (n_cols % bn == 0) return bn;
+  return 0;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int MODE, bool GEGLU, typename TC>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = tc_gemm_kernel<MODE, GEGLU, TC>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
+    configured = true;
+  }
+  int grid = p.m_tiles * p.n_tiles;
+  if (grid > num_sms()) grid = num_sms();
+  kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
+  PB_LAUNCH_CHECK("tc_gemm_kernel");
+  return PB_OK;
+}
+
+template <int MODE, bool GEGLU>
+static int launch_c(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, size_t smem, cudaStream_t st,
+                    int c_dtype) {
+  if (c_dtype == PB_F32) return launch<MODE, GEGLU, float>(a, b, p, smem, st);
+  return launch<MODE, GEGLU, bf16>(a, b, p, smem, st);
+}
+
+}  // namespace tc
+}  // namespace pb
+
+extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
+  using namespace pb;
+  using namespace pb::tc;
+  int rc = validate_gemm_args(a, "pb_tc_gemm");
+  if (rc != PB_OK) return rc;
+#define TC_UNSUPPORTED(...)      \
+  do {                           \
+    set_error(__VA_ARGS__);      \
+    return PB_EUNSUPPORTED;      \
+  } while (0)
+  if (a->a_dtype != PB_BF16) TC_UNSUPPORTED("pb_tc_gemm: operands must be bf16");
+  const bool geglu = (a->epilogue & PB_EPI_GEGLU) != 0;
+  if (a->N % 16 != 0 || (geglu && a->N % 32 != 0)) TC_UNSUPPORTED("pb_tc_gemm: N=%lld not a multiple of 16", (long long)a->N);
+  if (a->lda % 8 != 0) TC_UNSUPPORTED("pb_tc_gemm: lda must be a multiple of 8 (16-byte rows)");
+  if ((reinterpret_cast<uintptr_t>(a->a) | reinterpret_cast<uintptr_t>(a->w)) & 15)
+    TC_UNSUPPORTED("pb_tc_gemm: operands must be 16-byte aligned");
+  if (geglu && (a->epilogue & (PB_EPI_ROWBIAS | PB_EPI_RESIDUAL)))
+    TC_UNSUPPORTED("pb_tc_gemm: GEGLU cannot be combined with rowbias/residual");
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.c = a->c; p.bias = a->bias; p.rowbias = a->rowbias; p.residual = a->residual;
+  p.M = a->M; p.ldc = a->ldc; p.ldr = a->ldr; p.ldrb = a->ld_rowbias;
+  p.rb_rows = a->rowbias_rows > 0 ? a->rowbias_rows : 1;
+  p.N = (int)a->N; p.epi = a->epilogue;
+  p.geglu_half = geglu ? (int)(a->N / 2) : 0;
+
+  const int n_cols = geglu ? (int)(a->N / 2) : (int)a->N;   // output columns
+  int bn_out = pick_block_n(n_cols, geglu ? 128 : 256);
+  if (bn_out == 0) TC_UNSUPPORTED("pb_tc_gemm: no tile width divides N=%d", n_cols);
+  p.block_n = geglu ? 2 * bn_out : bn_out;
+  p.n_tiles = n_cols / bn_out;
+
+  CUtensorMap tmA, tmB;
+  const int cin = a->a_mode == PB_A_LINEAR ? (int)a->K : a->cin;
+  if (cin % BLOCK_K != 0) TC_UNSUPPORTED("pb_tc_gemm: K per tap (%d) must be a multiple of 64", cin);
+  p.k_chunks = cin / BLOCK_K;
+  const uint64_t esz = 2;
+  if (a->a_mode == PB_A_LINEAR) {
+    p.taps = 1;
+    p.m_tiles = (int)ceil_div(a->M, BLOCK_M);
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+    uint64_t str[1] = {(uint64_t)a->lda * esz};
+    uint32_t box[2] = {BLOCK_K, BLOCK_M};
+    rc = encode_tmap_bf16(&tmA, a->a, 2, dims, str, box);
+  } else if (a->a_mode == PB_A_CONV3X3) {
+    if (a->stride != 1 || a->upsample) TC_UNSUPPORTED("pb_tc_gemm: conv3x3 stride 2 / upsample not on the TMA path");
+    p.taps = 9;
+    const int W = a->in_w, H = a->in_h, n_img = (int)(a->M / ((int64_t)H * W));
+    p.W = W; p.H = H;
+    p.bw = largest_divisor_leq(W, BLOCK_M);
+    p.bh = largest_divisor_leq(H, BLOCK_M / p.bw);
+    p.bn_img = largest_divisor_leq(n_img, BLOCK_M / (p.bw * p.bh));
+    if (p.bw * p.bh * p.bn_img != BLOCK_M)
+      TC_UNSUPPORTED("pb_tc_gemm: %dx%d x %d images has no exact 128-row brick", H, W, n_img);
+    p.tiles_x = W / p.bw; p.tiles_y = H / p.bh;
+    p.m_tiles = p.tiles_x * p.tiles_y * (n_img / p.bn_img);
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
+    uint64_t str[3] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * W, (uint64_t)a->lda * esz * W * H};
+    uint32_t box[4] = {BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn_img};
+    rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box);
+  } else {
+    p.taps = 3;
+    const int HW = a->frame_rows, T = a->frames, nb = (int)(a->M / ((int64_t)HW * T));
+    p.W = HW; p.H = T; p.bn_img = 1;
+    p.bw = largest_divisor_leq(HW, BLOCK_M);
+    p.bh = largest_divisor_leq(T, BLOCK_M / p.bw);
+    if (p.bw * p.bh != BLOCK_M) TC_UNSUPPORTED("pb_tc_gemm: %d pixels x %d frames has no exact 128-row brick", HW, T);
+    p.tiles_x = HW / p.bw; p.tiles_y = T / p.bh;
+    p.m_tiles = p.tiles_x * p.tiles_y * nb;
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)HW, (uint64_t)T, (uint64_t)nb};
+    uint64_t str[3] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * HW, (uint64_t)a->lda * esz * HW * T};
+    uint32_t box[4] = {BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+    rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box);
+  }
+  if (rc != PB_OK) return rc;
+  {
+    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
+    uint64_t str[1] = {(uint64_t)a->K * esz};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)(geglu ? p.block_n / 2 : p.block_n)};
+    rc = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box);
+    if (rc != PB_OK) return rc;
+  }
+  const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+  p.stages = SMEM_BUDGET / stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * MAX_STAGES + 4) + 16;
+
+  cudaStream_t st = to_stream(stream);
+  const int cd = a->c_dtype;
+  if (a->a_mode == PB_A_LINEAR)
+    return geglu ? launch_c<PB_A_LINEAR, true>(tmA, tmB, p, smem, st, cd) : launch_c<PB_A_LINEAR, false>(tmA, tmB, p, smem, st, cd);
+  if (a->a_mode == PB_A_CONV3X3) return launch_c<PB_A_CONV3X3, false>(tmA, tmB, p, smem, st, cd);
+  return launch_c<PB_A_CONVT3, false>(tmA, tmB, p, smem, st, cd);
+#undef TC_UNSUPPORTED
 }

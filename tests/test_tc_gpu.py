@@ -1,0 +1,112 @@
+"""GPU: tcgen05/TMA kernels against fp64 PyTorch on the same bf16 operands (bit-level inputs shared)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_l2
+from test_kernels_gpu import conv_weight_rows, ref_attn, rnd
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def abi():
+    from pandora_b200 import abi as a
+    a.load()
+    if not a.supports_tc():
+        pytest.skip("device has no tcgen05")
+    return a
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 320, 320), (2560, 1280, 1280), (1232, 640, 1024),
+                                   (4096, 960, 320), (640, 256, 2560), (77, 192, 128)])
+@pytest.mark.parametrize("cdt", [torch.float32, BF])
+def test_tc_gemm_linear(abi, M, N, K, cdt):
+    a, w = rnd(M, K, seed=1, dtype=BF), rnd(N, K, seed=2, dtype=BF, scale=K ** -0.5)
+    bias, res = rnd(N, seed=3), rnd(M, N, seed=4)
+    c = torch.full((M, N), float("nan"), dtype=cdt, device="cuda")
+    assert abi.gemm(a, w, c, bias=bias, residual=res, tc=True)
+    ref = a.double() @ w.double().t() + bias.double() + res.double()
+    assert rel_l2(c, ref) < (3e-6 if cdt == torch.float32 else 4e-3)
+
+
+def test_tc_gemm_plain_and_rowbias_and_views(abi):
+    M, N, K = 512, 320, 192
+    big_a = rnd(M, K + 64, seed=5, dtype=BF)
+    a = big_a[:, 64:]
+    w = rnd(N, K, seed=6, dtype=BF, scale=K ** -0.5)
+    big_c = torch.zeros(M, N + 64, device="cuda")
+    c = big_c[:, 32:32 + N]
+    rb = rnd(4, N, seed=7)
+    assert abi.gemm(a, w, c, rowbias=rb, rowbias_rows=128, tc=True)
+    ref = a.double() @ w.double().t() + rb.double().repeat_interleave(128, 0)
+    assert rel_l2(c, ref) < 3e-6
+    assert float(big_c[:, :32].abs().max()) == 0 and float(big_c[:, 32 + N:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("M,C", [(256, 64), (1000, 320), (2560, 1280)])
+def test_tc_gemm_geglu(abi, M, C):
+    a = rnd(M, C, seed=8, dtype=BF)
+    w = rnd(8 * C, C, seed=9, dtype=BF, scale=C ** -0.5)
+    bias = rnd(8 * C, seed=10)
+    y = torch.empty(M, 4 * C, dtype=BF, device="cuda")
+    assert abi.gemm(a, w, y, bias=bias, geglu=True, tc=True)
+    u = a.double() @ w.double().t() + bias.double()
+    ref = u[:, :4 * C] * F.gelu(u[:, 4 * C:])
+    assert rel_l2(y, ref) < 4e-3
+
+
+@pytest.mark.parametrize("n,cin,cout,H,W", [(16, 64, 64, 8, 8), (16, 128, 64, 4, 4), (2, 320, 320, 40, 64),
+                                            (16, 640, 320, 10, 16), (16, 1280, 1280, 5, 8), (4, 64, 128, 20, 32),
+                                            (2, 64, 64, 18, 32), (1, 64, 64, 72, 128)])
+def test_tc_conv3x3(abi, n, cin, cout, H, W):
+    x = rnd(n, cin, H, W, seed=11, dtype=BF)
+    w = rnd(cout, cin, 3, 3, seed=12, dtype=BF, scale=(9 * cin) ** -0.5)
+    bias = rnd(cout, seed=13)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    rows = x.permute(0, 2, 3, 1).reshape(n * H * W, cin).contiguous()
+    emb = rnd(n // 2 if n > 1 else 1, cout, seed=14)
+    rb_rows = 2 * H * W if n > 1 else H * W
+    res = rnd(n * H * W, cout, seed=15)
+    c = torch.full((n * H * W, cout), float("nan"), device="cuda")
+    ok = abi.gemm(rows, conv_weight_rows(w), c, bias=bias, residual=res, rowbias=emb, rowbias_rows=rb_rows,
+                  mode=abi.A_CONV3X3, conv=(cin, H, W, H, W, 1, 0), tc=True)
+    assert ok, "expected the TMA path to take this shape"
+    ref_rows = ref.permute(0, 2, 3, 1).reshape(n * H * W, cout) + res.double() \
+        + emb.double().repeat_interleave(rb_rows, 0)
+    assert rel_l2(c, ref_rows) < 3e-6
+
+
+def test_tc_conv3x3_declines_what_it_cannot_tile(abi):
+    rows = rnd(16 * 2 * 2, 64, seed=16, dtype=BF)
+    w = rnd(64, 9 * 64, seed=17, dtype=BF)
+    c = torch.empty(64, 64, device="cuda")
+    assert abi.gemm(rows, w, c, mode=abi.A_CONV3X3, conv=(64, 2, 2, 2, 2, 1, 0), tc=True) is False
+    assert abi.gemm(rows, w, c[:16], mode=abi.A_CONV3X3, conv=(64, 2, 2, 1, 1, 2, 0), tc=True, M=16) is False
+
+
+@pytest.mark.parametrize("b,T,HW,C", [(1, 16, 160, 320), (2, 16, 64, 64), (1, 16, 40, 1280), (1, 16, 2560, 64),
+                                      (1, 16, 16, 128)])
+def test_tc_convt3(abi, b, T, HW, C):
+    x = rnd(b, C, T, HW, 1, seed=18, dtype=BF)
+    w = rnd(C, C, 3, 1, 1, seed=19, dtype=BF, scale=(3 * C) ** -0.5)
+    bias = rnd(C, seed=20)
+    ref = F.conv3d(x.double(), w.double(), bias.double(), padding=(1, 0, 0))
+    rows = x[..., 0].permute(0, 2, 3, 1).reshape(b * T * HW, C).contiguous()
+    wr = w[:, :, :, 0, 0].permute(0, 2, 1).reshape(C, 3 * C).contiguous()
+    res = rnd(b * T * HW, C, seed=21)
+    c = torch.full((b * T * HW, C), float("nan"), device="cuda")
+    assert abi.gemm(rows, wr, c, bias=bias, residual=res, mode=abi.A_CONVT3, convt=(C, T, HW), tc=True)
+    ref_rows = ref[..., 0].permute(0, 2, 3, 1).reshape(b * T * HW, C) + res.double()
+    assert rel_l2(c, ref_rows) < 3e-6
+
+
+def test_tc_gemm_back_to_back_launches_are_deterministic(abi):
+    a, w = rnd(5000, 640, seed=22, dtype=BF), rnd(640, 640, seed=23, dtype=BF, scale=640 ** -0.5)
+    outs = []
+    for _ in range(3):
+        c = torch.empty(5000, 640, device="cuda")
+        abi.gemm(a, w, c, tc=True)
+        outs.append(c)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
