@@ -102,16 +102,18 @@ int pb_tc_gemm(const pb_gemm_args* args, pb_stream_t stream);
  * attention.py:265,331 (eps 1e-6) plus the following nn.SiLU.  x is rows [n_inst*rows_per_inst, C];
  * statistics are taken per (instance, group) over rows_per_inst x C/groups elements: an instance is
  * one frame for the 2-D blocks and all T frames of a sample for the temporal blocks.
- * pb_groupnorm_stats writes mean/rstd [n_inst, groups] fp32 (workspace: pb_groupnorm_ws_bytes).   */
+ * pb_groupnorm_stats reduces the statistics and folds them with the affine parameters into
+ * scale_shift [n_inst, 2, C] fp32 (y = x*scale + shift); pb_groupnorm_apply streams x once more,
+ * applies it (+SiLU) and writes the operand dtype of the consuming GEMM.
+ * Workspace for the partial sums: pb_groupnorm_ws_bytes.                                          */
 size_t pb_groupnorm_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int64_t C);
 int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_inst,
-                       int64_t rows_per_inst, int64_t C, int32_t groups, float eps,
-                       float* mean_rstd /* [n_inst, groups, 2] */, void* ws, size_t ws_bytes,
-                       pb_stream_t stream);
+                       int64_t rows_per_inst, int64_t C, int32_t groups, float eps, const float* gamma,
+                       const float* beta, float* scale_shift /* [n_inst, 2, C] */, void* ws,
+                       size_t ws_bytes, pb_stream_t stream);
 int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype,
                        int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
-                       int32_t groups, const float* mean_rstd, const float* gamma,
-                       const float* beta, int32_t silu, pb_stream_t stream);
+                       const float* scale_shift, int32_t silu, pb_stream_t stream);
 
 /* ---- LayerNorm ---------------------------------------------------------------------------------
  * Replaces nn.LayerNorm(dim) eps 1e-5 at attention.py:225-227,243-245.                            */
@@ -158,6 +160,11 @@ int pb_add(const float* a, const float* b, float* y, int64_t n, pb_stream_t stre
  * (openaimodel3d.py:600) and fp32-trunk -> operand casts                                          */
 int pb_copy_rows(const void* src, int32_t s_dtype, int64_t lds, void* dst, int32_t d_dtype,
                  int64_t ldd, int64_t rows, int64_t cols, pb_stream_t stream);
+/* nearest x2 upsample of NHWC rows [n_img*H*W, cols] -> [n_img*2H*2W, cols] with dtype conversion
+ * (Upsample, openaimodel3d.py:98-109; feeds the tcgen05 conv, pb_gemm folds it instead)           */
+int pb_upsample2x_rows(const void* src, int32_t s_dtype, int64_t lds, void* dst, int32_t d_dtype,
+                       int64_t ldd, int64_t n_img, int64_t H, int64_t W, int64_t cols,
+                       pb_stream_t stream);
 /* sinusoidal embedding with a caller-supplied frequency table (utils_diffusion.py:8-28; the table
  * is the bf16-evaluated one, uploaded as fp32): out[b, :half]=cos(t*f), out[b, half:]=sin(t*f)   */
 int pb_timestep_embedding(const int64_t* t, const float* freqs, float* out, int64_t batch,

@@ -1,0 +1,331 @@
+// attention_tc.cu — tcgen05 flash attention, head_dim 64, bf16 operands, fp32 softmax/accumulation.
+//
+// One CTA per (batch, head, 128-query tile); 192 threads, warp-specialised:
+//   warp 0      TMA producer : Q tile once, then K_j / V_j tiles (128 keys x 64) through a 3-stage ring
+//   warp 1      MMA issuer   : S_j = Q K_j^T  (UMMA 128x128x64, both operands K-major, -> TMEM, 2 buffers)
+//                              O_j = P_j V_j  (UMMA 128x64x128, A = P_j from shared memory, B = V_j used
+//                              MN-major straight from its row-major [key][d] tile, -> TMEM, 2 buffers)
+//   warps 2..5  softmax      : one thread per query row (a TMEM lane): two passes over S_j in TMEM
+//                              (row max, then p = exp2(s*scale - m)), P_j written to shared memory as the
+//                              swizzled bf16 A operand, O_j pulled from TMEM and folded into a register
+//                              accumulator with the online-softmax correction.
+// S_{j+1} is issued before the softmax of tile j finishes, so tensor and MUFU/ALU work overlap.
+// Key masking handles n_kv that is not a multiple of 128 (77 text / 16 image tokens, 160, 40, ...).
+#include <math.h>
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace pb {
+namespace tc {
+
+constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64;
+constexpr int KV_STAGES = 3;
+constexpr int ATT_THREADS = 192;
+constexpr int UMMA_K = 16;
+constexpr int TILE_BYTES = 128 * 64 * 2;      // 16 KiB: one [128 x 64] bf16 tile
+constexpr int P_BYTES = 2 * TILE_BYTES;       // [128 x 128] bf16 as two K-blocks
+constexpr int ATT_SMEM = TILE_BYTES * (1 + 2 * KV_STAGES) + 2 * P_BYTES;   // 176 KiB
+constexpr int S_COL0 = 0, O_COL0 = 256;       // TMEM columns: S buffers at 0/128, O buffers at 256/320
+
+struct AttP {
+  void* out;
+  int64_t o_bdiv, o_bso, o_bsi, o_rs;
+  int q_bdiv, k_bdiv, v_bdiv;
+  int nq, nkv, kv_tiles;
+  float scale_log2;
+  int accumulate;
+};
+
+// MN-major B operand tile [k rows][64 contiguous n], 128-byte swizzle: 8-row K groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 16;   // LBO: stride between 64-wide N blocks (single block here)
+  d |= (uint64_t)(1024 >> 4) << 32;   // SBO: stride between 8-row K groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttP p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  auto sK = [&](int s) { return base + TILE_BYTES * (1 + s); };
+  auto sV = [&](int s) { return base + TILE_BYTES * (1 + KV_STAGES + s); };
+  auto sP = [&](int b) { return base + TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES * b; };
+  const uint32_t bars = base + ATT_SMEM;
+  const uint32_t q_full = bars;
+  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (1 + KV_STAGES + s); };
+  auto s_full = [&](int b) { return bars + 8u * (1 + 2 * KV_STAGES + b); };
+  auto p_full = [&](int b) { return bars + 8u * (3 + 2 * KV_STAGES + b); };
+  auto o_full = [&](int b) { return bars + 8u * (5 + 2 * KV_STAGES + b); };
+  const uint32_t tmem_slot = bars + 8u * (7 + 2 * KV_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
+  const int n_tiles = p.kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 128); mbar_init(o_full(b), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, head * ATT_D, q_tile * ATT_BM, n / p.q_bdiv);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % KV_STAGES;
+        mbar_wait(kv_empty(s), ((j / KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(kv_full(s), 2 * TILE_BYTES);
+        tma_load_3d(sK(s), &tmK, kv_full(s), head * ATT_D, j * ATT_BN, n / p.k_bdiv);
+        tma_load_3d(sV(s), &tmV, kv_full(s), head * ATT_D, j * ATT_BN, n / p.v_bdiv);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN);                 // K-major A and B
+      const uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);     // B (= V) MN-major
+      const uint64_t q_desc = make_smem_desc_sw128(sQ);
+      auto issue_s = [&](int j) {
+        const int s = j % KV_STAGES;
+        mbar_wait(kv_full(s), (j / KV_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t k_desc = make_smem_desc_sw128(sK(s));
+        const uint32_t d = tmem_base + S_COL0 + (uint32_t)(j & 1) * ATT_BN;
+#pragma unroll
+        for (int k = 0; k < ATT_D / UMMA_K; ++k) umma_bf16(d, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full(j & 1));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (n_tiles > 1) issue_s(1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % KV_STAGES, b = j & 1;
+        mbar_wait(p_full(b), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + O_COL0 + (uint32_t)b * ATT_D;
+#pragma unroll
+        for (int k = 0; k < ATT_BN / UMMA_K; ++k) {
+          // A: P block k/4 (16 KiB apart), 32 B per k-step inside the swizzled row; B: 16 key rows = 2 KiB per step
+          const uint64_t a_desc = make_smem_desc_sw128(sP(b) + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
+          const uint64_t b_desc = make_smem_desc_mn_sw128(sV(s) + k * 16 * 128);
+          umma_bf16(d, a_desc, b_desc, idesc_o, k != 0);
+        }
+        umma_commit(o_full(b));
+        umma_commit(kv_empty(s));
+        if (j + 2 < n_tiles) issue_s(j + 2);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + output (warps 2..5)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float acc[ATT_D];
+#pragma unroll
+    for (int i = 0; i < ATT_D; ++i) acc[i] = 0.f;
+    float m_run = -INFINITY, m_acc = -INFINITY, l = 0.f;
+
+    auto fold_o = [&](int t, float m_t) {
+      mbar_wait(o_full(t & 1), (t >> 1) & 1);
+      tc_fence_after();
+      const float corr = exp2f(m_acc - m_t);   // 0 on the first tile (m_acc = -inf)
+      m_acc = m_t;
+#pragma unroll
+      for (int c = 0; c < ATT_D; c += 32) {
+        float o[32];
+        tmem_ld32(lane_addr + O_COL0 + (uint32_t)(t & 1) * ATT_D + c, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], corr, o[i]);
+      }
+    };
+
+    float m_prev_tile = -INFINITY;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int b = j & 1;
+      const int valid = p.nkv - j * ATT_BN;       // keys of this tile that exist (>= 1)
+      mbar_wait(s_full(b), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = lane_addr + S_COL0 + (uint32_t)b * ATT_BN;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < ATT_BN; c += 32) {
+        float v[32];
+        tmem_ld32(s_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < valid) ? v[i] : -INFINITY);
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      l *= exp2f(m_run - m_new);
+      m_run = m_new;
+      const uint32_t p_row = sP(b) + (uint32_t)r * 128;
+#pragma unroll
+      for (int c = 0; c < ATT_BN; c += 32) {
+        float v[32];
+        tmem_ld32(s_addr + c, v);
+        tmem_ld_wait();
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = (c + i < valid) ? exp2f(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
+          const float p1 = (c + i + 1 < valid) ? exp2f(fmaf(v[i + 1], p.scale_log2, -m_new)) : 0.f;
+          l += p0 + p1;
+          w[i >> 1] = pack_bf16(p0, p1);
+        }
+        // 32 keys = 64 B = 4 chunks of 16 B; K-block (c / 64), chunk index within the 128-byte row
+        const uint32_t blk = p_row + (uint32_t)(c >> 6) * TILE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t chunk = (uint32_t)(((c & 63) >> 3) + q);
+          const uint32_t addr = blk + ((chunk ^ (uint32_t)(r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * q]), "r"(w[4 * q + 1]),
+                       "r"(w[4 * q + 2]), "r"(w[4 * q + 3])
+                       : "memory");
+        }
+      }
+      fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full(b));
+      if (j > 0) fold_o(j - 1, m_prev_tile);
+      m_prev_tile = m_new;
+    }
+    fold_o(n_tiles - 1, m_prev_tile);
+
+    const int64_t qi = (int64_t)q_tile * ATT_BM + r;
+    if (qi < p.nq) {
+      const float inv = 1.0f / l;
+      bf16* O = reinterpret_cast<bf16*>(p.out) + (n / p.o_bdiv) * p.o_bso + (n % p.o_bdiv) * p.o_bsi + qi * p.o_rs +
+                head * ATT_D;
+#pragma unroll
+      for (int c = 0; c < ATT_D; c += 8) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = acc[c + i] * inv;
+        uint4* dst = reinterpret_cast<uint4*>(O + c);
+        if (p.accumulate) {
+          uint4 prev = *dst;
+          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { o[2 * i] += __low2float(pv[i]); o[2 * i + 1] += __high2float(pv[i]); }
+        }
+        uint4 val;
+        val.x = pack_bf16(o[0], o[1]); val.y = pack_bf16(o[2], o[3]);
+        val.z = pack_bf16(o[4], o[5]); val.w = pack_bf16(o[6], o[7]);
+        *dst = val;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int encode_rows3d(CUtensorMap* m, const pb_attn_operand& o, int64_t cols, int64_t rows, int64_t n_batch) {
+  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)rows, (uint64_t)(n_batch < 1 ? 1 : n_batch)};
+  uint64_t bs = o.bs_outer > 0 ? (uint64_t)o.bs_outer : (uint64_t)rows * o.rs;
+  uint64_t str[2] = {(uint64_t)o.rs * 2, bs * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return encode_tmap_bf16(m, o.ptr, 3, dims, str, box);
+}
+
+}  // namespace tc
+}  // namespace pb
+
+extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
+  using namespace pb;
+  using namespace pb::tc;
+  int rc = validate_attn_args(a, "pb_tc_attention");
+  if (rc != PB_OK) return rc;
+#define ATT_UNSUPPORTED(...)   \
+  do {                         \
+    set_error(__VA_ARGS__);    \
+    return PB_EUNSUPPORTED;    \
+  } while (0)
+  if (a->dtype != PB_BF16) ATT_UNSUPPORTED("pb_tc_attention: bf16 only");
+  if (a->q.bs_inner != 0 || a->k.bs_inner != 0 || a->v.bs_inner != 0)
+    ATT_UNSUPPORTED("pb_tc_attention: strided (temporal) batches use the dedicated kernel");
+  if (a->n_q < 64) ATT_UNSUPPORTED("pb_tc_attention: n_q < 64 is served by the CUDA-core kernel");
+  if ((a->q.rs | a->k.rs | a->v.rs | a->o_rs) % 8 != 0 || (a->q.bs_outer | a->k.bs_outer | a->v.bs_outer) % 8 != 0)
+    ATT_UNSUPPORTED("pb_tc_attention: strides must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(a->q.ptr) | reinterpret_cast<uintptr_t>(a->k.ptr) |
+       reinterpret_cast<uintptr_t>(a->v.ptr) | reinterpret_cast<uintptr_t>(a->out)) & 15)
+    ATT_UNSUPPORTED("pb_tc_attention: operands must be 16-byte aligned");
+  if (a->batch > 65535 || a->heads > 65535) ATT_UNSUPPORTED("pb_tc_attention: grid too large");
+
+  CUtensorMap tq, tk, tv;
+  const int64_t cols = a->heads * 64;
+  if ((rc = encode_rows3d(&tq, a->q, cols, a->n_q, ceil_div(a->batch, a->q.bdiv))) != PB_OK) return rc;
+  if ((rc = encode_rows3d(&tk, a->k, cols, a->n_kv, ceil_div(a->batch, a->k.bdiv))) != PB_OK) return rc;
+  if ((rc = encode_rows3d(&tv, a->v, cols, a->n_kv, ceil_div(a->batch, a->v.bdiv))) != PB_OK) return rc;
+
+  AttP p;
+  memset(&p, 0, sizeof(p));
+  p.out = a->out;
+  p.o_bdiv = a->o_bdiv; p.o_bso = a->o_bs_outer; p.o_bsi = a->o_bs_inner; p.o_rs = a->o_rs;
+  p.q_bdiv = (int)a->q.bdiv; p.k_bdiv = (int)a->k.bdiv; p.v_bdiv = (int)a->v.bdiv;
+  p.nq = (int)a->n_q; p.nkv = (int)a->n_kv;
+  p.kv_tiles = (int)ceil_div(a->n_kv, ATT_BN);
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.accumulate = a->accumulate;
+
+  static bool configured = false;
+  const size_t smem = ATT_SMEM + 1024 + 8 * (8 + 2 * KV_STAGES) + 16;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attention_kernel)");
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM), (unsigned)a->heads, (unsigned)a->batch);
+  tc_attention_kernel<<<grid, ATT_THREADS, smem, to_stream(stream)>>>(tq, tk, tv, p);
+  PB_LAUNCH_CHECK("tc_attention_kernel");
+  return PB_OK;
+#undef ATT_UNSUPPORTED
+}

@@ -55,6 +55,26 @@ __global__ void copy_rows_kernel(const TS* __restrict__ s, int64_t lds, TD* __re
   }
 }
 
+// nearest-neighbour x2 upsample of NHWC rows (openaimodel3d.py:98-109), with dtype conversion
+template <typename TS, typename TD>
+__global__ void upsample2x_kernel(const TS* __restrict__ s, int64_t lds, TD* __restrict__ d, int64_t ldd,
+                                  int H, int W, int64_t cols, int64_t total_vec) {
+  const int64_t cv = cols >> 2;
+  const int W2 = 2 * W, H2 = 2 * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t orow = i / cv, v = i - orow * cv;
+    const int ox = (int)(orow % W2);
+    const int64_t t = orow / W2;
+    const int oy = (int)(t % H2);
+    const int64_t n = t / H2;
+    const int64_t irow = (n * H + (oy >> 1)) * W + (ox >> 1);
+    float x[4];
+    load4(s + irow * lds + v * 4, x);
+    store4(d + orow * ldd + v * 4, x);
+  }
+}
+
 // out[b, j] = cos(t_b * f_j), out[b, half + j] = sin(t_b * f_j); precise cosf/sinf (arguments reach ~1e3)
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
                                           float* __restrict__ out, int64_t batch, int64_t half) {
@@ -218,6 +238,23 @@ int pb_copy_rows(const void* src, int32_t s_dtype, int64_t lds, void* dst, int32
     })
   })
   PB_LAUNCH_CHECK("copy_rows_kernel");
+  return PB_OK;
+}
+
+int pb_upsample2x_rows(const void* src, int32_t s_dtype, int64_t lds, void* dst, int32_t d_dtype, int64_t ldd,
+                       int64_t n_img, int64_t H, int64_t W, int64_t cols, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(src && dst && n_img > 0 && H > 0 && W > 0 && cols > 0, "pb_upsample2x_rows: bad arguments");
+  PB_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "pb_upsample2x_rows: sizes must be multiples of 4");
+  const int64_t total = n_img * 4 * H * W * (cols / 4);
+  cudaStream_t st = to_stream(stream);
+  PB_DISPATCH_DTYPE(s_dtype, TS, {
+    PB_DISPATCH_DTYPE(d_dtype, TD, {
+      upsample2x_kernel<TS, TD><<<grid_for(total), 256, 0, st>>>(reinterpret_cast<const TS*>(src), lds,
+                                                                 reinterpret_cast<TD*>(dst), ldd, (int)H, (int)W, cols, total);
+    })
+  })
+  PB_LAUNCH_CHECK("upsample2x_kernel");
   return PB_OK;
 }
 

@@ -285,10 +285,19 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   return PB_OK;
 }
 
-static int largest_divisor_leq(int n, int cap) {
-  for (int d = cap < n ? cap : n; d >= 1; --d)
-    if (n % d == 0) return d;
-  return 1;
+// Exact 128-row brick bw x bh x bn with bw | W, bh | H, bn | N; prefers wide bricks (long contiguous
+// runs for the TMA unit).  Returns false when the tensor cannot be tiled exactly.
+static bool pick_brick(int W, int H, int N, int* bw, int* bh, int* bn) {
+  for (int w = W < BLOCK_M ? W : BLOCK_M; w >= 1; --w) {
+    if (W % w != 0 || BLOCK_M % w != 0) continue;
+    const int rest = BLOCK_M / w;
+    for (int h = H < rest ? H : rest; h >= 1; --h) {
+      if (H % h != 0 || rest % h != 0) continue;
+      const int n = rest / h;
+      if (n <= N && N % n == 0) { *bw = w; *bh = h; *bn = n; return true; }
+    }
+  }
+  return false;
 }
 
 static int pick_block_n(int n_cols, int cap) {
@@ -385,10 +394,7 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     p.taps = 9;
     const int W = a->in_w, H = a->in_h, n_img = (int)(a->M / ((int64_t)H * W));
     p.W = W; p.H = H;
-    p.bw = largest_divisor_leq(W, BLOCK_M);
-    p.bh = largest_divisor_leq(H, BLOCK_M / p.bw);
-    p.bn_img = largest_divisor_leq(n_img, BLOCK_M / (p.bw * p.bh));
-    if (p.bw * p.bh * p.bn_img != BLOCK_M)
+    if (!pick_brick(W, H, n_img, &p.bw, &p.bh, &p.bn_img))
       TC_UNSUPPORTED("pb_tc_gemm: %dx%d x %d images has no exact 128-row brick", H, W, n_img);
     p.tiles_x = W / p.bw; p.tiles_y = H / p.bh;
     p.m_tiles = p.tiles_x * p.tiles_y * (n_img / p.bn_img);
@@ -400,9 +406,8 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     p.taps = 3;
     const int HW = a->frame_rows, T = a->frames, nb = (int)(a->M / ((int64_t)HW * T));
     p.W = HW; p.H = T; p.bn_img = 1;
-    p.bw = largest_divisor_leq(HW, BLOCK_M);
-    p.bh = largest_divisor_leq(T, BLOCK_M / p.bw);
-    if (p.bw * p.bh != BLOCK_M) TC_UNSUPPORTED("pb_tc_gemm: %d pixels x %d frames has no exact 128-row brick", HW, T);
+    int one = 1;
+    if (!pick_brick(HW, T, 1, &p.bw, &p.bh, &one)) TC_UNSUPPORTED("pb_tc_gemm: %d pixels x %d frames has no exact 128-row brick", HW, T);
     p.tiles_x = HW / p.bw; p.tiles_y = T / p.bh;
     p.m_tiles = p.tiles_x * p.tiles_y * nb;
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)HW, (uint64_t)T, (uint64_t)nb};

@@ -3,84 +3,99 @@
 // GroupNorm (basics.py:76-88; openaimodel3d.py:155,179,259-268,547; attention.py:265,331):
 //   rows layout [n_inst * R, C]; statistics per (instance, group) over R rows x C/G channels.
 //   Pass 1  gn_partial_kernel : grid (splits, n_inst); every thread owns one 4-channel vector
-//           column and walks rows with a fixed stride, so loads are fully coalesced and the
-//           accumulators live in registers; per-channel partial (sum, sumsq) go to the workspace.
+//           column and walks rows with a fixed stride (4 loads in flight), so loads are fully
+//           coalesced and the accumulators live in registers; per-channel partial (sum, sumsq) go to
+//           the workspace.
 //   Pass 2  gn_finalize_kernel: one warp per (instance, group) folds splits x C/G partials in fp64
-//           -> mean, rstd.
-//   Pass 3  gn_apply_kernel   : y = (x-mean)*rstd*gamma+beta (+SiLU), vectorised, written in the
-//           operand dtype the next GEMM wants (bf16 or fp32).
+//           -> mean, rstd -> per-channel (scale, shift).
+//   Pass 3  gn_apply_kernel   : y = x*scale + shift (+SiLU), vectorised, no integer division in the
+//           loop, written in the operand dtype the next GEMM wants (bf16 or fp32).
 // LayerNorm (attention.py:225-227): one warp per row, two-pass in registers.
 #include "common.cuh"
 
 namespace pb {
 
 constexpr int GN_THREADS = 256;
+constexpr int GN_APPLY_ROWS = 32;   // rows per CTA in the apply pass
+
+// Thread mapping shared by both passes: TX threads across 4-channel vector columns, TY row lanes.
+// A thread keeps its column(s) for the whole CTA lifetime, so per-column data sits in registers and the
+// inner loops contain no integer division.
+static inline void gn_shape(int cv, int* TX, int* TY) {
+  *TX = cv < GN_THREADS ? cv : GN_THREADS;
+  *TY = GN_THREADS / *TX;
+}
 
 static inline int gn_splits(int64_t n_inst, int64_t R) {
-  // enough CTAs to fill 148 SMs a few times over, but at least 8 rows per CTA
-  int64_t want = ceil_div(148 * 4, n_inst);
+  // ~8 CTAs per SM overall, at least 8 rows per CTA
+  int64_t want = ceil_div(148 * 8, n_inst);
   int64_t maxs = ceil_div(R, 8);
   int64_t s = want < 1 ? 1 : want;
   if (s > maxs) s = maxs;
-  if (s > 1024) s = 1024;
+  if (s > 2048) s = 2048;
   return (int)s;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-gn_partial_kernel(const T* __restrict__ x, int64_t ldx, int64_t R, int C, int splits,
+gn_partial_kernel(const T* __restrict__ x, int64_t ldx, int64_t R, int C, int splits, int TX, int TY,
                   float* __restrict__ ws /* [n_inst, splits, C, 2] */) {
+  __shared__ float red[GN_THREADS * 8];
   const int inst = blockIdx.y, sp = blockIdx.x;
-  const int cv = C >> 2;                       // vectors per row
-  const int lanes = GN_THREADS / cv > 0 ? GN_THREADS / cv : 1;   // row lanes per CTA
+  const int cv = C >> 2;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const int64_t r_begin = R * sp / splits, r_end = R * (sp + 1) / splits;
   const T* base = x + (int64_t)inst * R * ldx;
   float* out = ws + ((int64_t)inst * splits + sp) * C * 2;
-  extern __shared__ float red[];               // [lanes][C][2] when lanes > 1
-
-  // cv may exceed the CTA (C=2560 -> 640 vectors): loop over vector columns
-  for (int v0 = 0; v0 < cv; v0 += GN_THREADS) {
-    int v, lane;
-    if (cv >= GN_THREADS) { v = v0 + threadIdx.x; lane = 0; }
-    else { v = threadIdx.x % cv; lane = threadIdx.x / cv; }
+  for (int v0 = 0; v0 < cv; v0 += TX) {
+    const int v = v0 + tx;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool active = (v < cv) && (lane < lanes);
-    if (active) {
-      const int step = cv >= GN_THREADS ? 1 : lanes;
-      for (int64_t r = r_begin + lane; r < r_end; r += step) {
+    if (v < cv && ty < TY) {
+      const T* col = base + (int64_t)v * 4;
+      int64_t r = r_begin + ty;
+      for (; r + 3 * TY < r_end; r += 4 * TY) {       // 4 independent loads in flight
+        float t0[4], t1[4], t2[4], t3[4];
+        load4(col + r * ldx, t0);
+        load4(col + (r + TY) * ldx, t1);
+        load4(col + (r + 2 * TY) * ldx, t2);
+        load4(col + (r + 3 * TY) * ldx, t3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s[i] += (t0[i] + t1[i]) + (t2[i] + t3[i]);
+          q[i] += (t0[i] * t0[i] + t1[i] * t1[i]) + (t2[i] * t2[i] + t3[i] * t3[i]);
+        }
+      }
+      for (; r < r_end; r += TY) {
         float t[4];
-        load4(base + r * ldx + (int64_t)v * 4, t);
+        load4(col + r * ldx, t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { s[i] += t[i]; q[i] = fmaf(t[i], t[i], q[i]); }
       }
     }
-    if (cv >= GN_THREADS) {
-      if (active) {
+    if (TY > 1) {
+      __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { out[(v * 4 + i) * 2] = s[i]; out[(v * 4 + i) * 2 + 1] = q[i]; }
-      }
-    } else {
-      // fold the row lanes through shared memory
-      if (active) {
+      for (int i = 0; i < 4; ++i) { red[threadIdx.x * 8 + i] = s[i]; red[threadIdx.x * 8 + 4 + i] = q[i]; }
+      __syncthreads();
+      if (ty == 0 && v < cv) {
+        for (int l = 1; l < TY; ++l) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          red[((lane * C) + v * 4 + i) * 2] = s[i];
-          red[((lane * C) + v * 4 + i) * 2 + 1] = q[i];
+          for (int i = 0; i < 4; ++i) { s[i] += red[(l * TX + tx) * 8 + i]; q[i] += red[(l * TX + tx) * 8 + 4 + i]; }
         }
       }
-      __syncthreads();
-      for (int c = threadIdx.x; c < C; c += GN_THREADS) {
-        float ss = 0.f, qq = 0.f;
-        for (int l = 0; l < lanes; ++l) { ss += red[(l * C + c) * 2]; qq += red[(l * C + c) * 2 + 1]; }
-        out[c * 2] = ss; out[c * 2 + 1] = qq;
-      }
-      break;  // cv < GN_THREADS: single pass
+    }
+    if (ty == 0 && v < cv) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { out[(v * 4 + i) * 2] = s[i]; out[(v * 4 + i) * 2 + 1] = q[i]; }
     }
   }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64_t R,
-                                   float eps, float* __restrict__ mean_rstd, int total) {
+// One warp per (instance, group): fold the partials in fp64 -> mean, rstd, then emit the per-channel
+// affine  y = x * scale + shift  (scale = rstd*gamma, shift = beta - mean*rstd*gamma).
+__global__ void gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64_t R, float eps,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ scale_shift /* [n_inst, 2, C] */, int total) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= total) return;
   const int inst = warp / G, g = warp % G;
@@ -97,40 +112,48 @@ __global__ void gn_finalize_kernel(const float* __restrict__ ws, int splits, int
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
-  if (lane == 0) {
-    double cnt = (double)R * cpg;
-    double mean = s / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    mean_rstd[((int64_t)inst * G + g) * 2] = (float)mean;
-    mean_rstd[((int64_t)inst * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  const double cnt = (double)R * cpg;
+  const double mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float meanf = (float)mean;
+  float* sc = scale_shift + (int64_t)inst * 2 * C;
+  for (int i = lane; i < cpg; i += 32) {
+    const int c = g * cpg + i;
+    const float a = rstd * gamma[c];
+    sc[c] = a;
+    sc[C + c] = beta[c] - meanf * a;
   }
 }
 
-template <typename TX, typename TY>
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y, int64_t ldy, int64_t R,
-                int C, int G, const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
-                const float* __restrict__ beta, int silu, int64_t total_vec) {
-  const int cv = C >> 2, cpg = C / G;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / cv;
-    const int v = (int)(i - row * cv);
-    const int64_t inst = row / R;
-    float t[4], g4[4], b4[4], o[4];
-    load4(x + row * ldx + (int64_t)v * 4, t);
-    load4(gamma + v * 4, g4);
-    load4(beta + v * 4, b4);
+template <typename TX_, typename TY_>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int64_t R, int C,
+                const float* __restrict__ scale_shift, int silu, int TX, int TY) {
+  const int inst = blockIdx.y;
+  const int cv = C >> 2;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  if (ty >= TY) return;
+  const int64_t r_begin = (int64_t)blockIdx.x * GN_APPLY_ROWS;
+  const int64_t r_end = r_begin + GN_APPLY_ROWS < R ? r_begin + GN_APPLY_ROWS : R;
+  const float* sc = scale_shift + (int64_t)inst * 2 * C;
+  const TX_* xb = x + (int64_t)inst * R * ldx;
+  TY_* yb = y + (int64_t)inst * R * ldy;
+  for (int v = tx; v < cv; v += TX) {
+    float a[4], b[4];
+    load4(sc + v * 4, a);
+    load4(sc + C + v * 4, b);
+    for (int64_t r = r_begin + ty; r < r_end; r += TY) {
+      float t[4], o[4];
+      load4(xb + r * ldx + (int64_t)v * 4, t);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int grp = (v * 4 + j) / cpg;
-      const float mean = __ldg(mean_rstd + (inst * G + grp) * 2);
-      const float rstd = __ldg(mean_rstd + (inst * G + grp) * 2 + 1);
-      float u = (t[j] - mean) * rstd * g4[j] + b4[j];
-      o[j] = silu ? silu_f(u) : u;
+      for (int j = 0; j < 4; ++j) {
+        const float u = fmaf(t[j], a[j], b[j]);
+        o[j] = silu ? silu_f(u) : u;
+      }
+      store4(yb + r * ldy + (int64_t)v * 4, o);
     }
-    store4(y + row * ldy + (int64_t)v * 4, o);
   }
 }
 
@@ -191,10 +214,10 @@ size_t pb_groupnorm_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int64_t C) {
 }
 
 int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_inst,
-                       int64_t rows_per_inst, int64_t C, int32_t groups, float eps,
-                       float* mean_rstd, void* ws, size_t ws_bytes, pb_stream_t stream) {
+                       int64_t rows_per_inst, int64_t C, int32_t groups, float eps, const float* gamma,
+                       const float* beta, float* scale_shift, void* ws, size_t ws_bytes, pb_stream_t stream) {
   using namespace pb;
-  PB_REQUIRE(x && mean_rstd && ws, "pb_groupnorm_stats: null pointer");
+  PB_REQUIRE(x && scale_shift && ws && gamma && beta, "pb_groupnorm_stats: null pointer");
   PB_REQUIRE(n_inst > 0 && rows_per_inst > 0 && C > 0 && groups > 0, "pb_groupnorm_stats: empty input");
   PB_REQUIRE(C % 4 == 0 && C % groups == 0 && ldx % 4 == 0,
              "pb_groupnorm_stats: need C %% 4 == 0, C %% groups == 0, ldx %% 4 == 0 (C=%lld)", (long long)C);
@@ -203,41 +226,37 @@ int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_in
   PB_REQUIRE(ws_bytes >= pb_groupnorm_ws_bytes(n_inst, rows_per_inst, C),
              "pb_groupnorm_stats: workspace too small");
   cudaStream_t st = to_stream(stream);
-  const int cv = (int)(C / 4);
-  const int lanes = cv >= GN_THREADS ? 1 : GN_THREADS / cv;
-  const size_t smem = cv >= GN_THREADS ? 0 : (size_t)lanes * C * 2 * sizeof(float);
-  PB_REQUIRE(smem <= 48 * 1024, "pb_groupnorm_stats: C=%lld needs %zu B smem", (long long)C, smem);
+  int TX, TY;
+  gn_shape((int)(C / 4), &TX, &TY);
   dim3 grid(splits, (unsigned)n_inst);
   PB_DISPATCH_DTYPE(x_dtype, T, {
-    gn_partial_kernel<T><<<grid, GN_THREADS, smem, st>>>(reinterpret_cast<const T*>(x), ldx, rows_per_inst,
-                                                         (int)C, splits, reinterpret_cast<float*>(ws));
+    gn_partial_kernel<T><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const T*>(x), ldx, rows_per_inst, (int)C,
+                                                      splits, TX, TY, reinterpret_cast<float*>(ws));
   })
   PB_LAUNCH_CHECK("gn_partial_kernel");
   const int total = (int)(n_inst * groups);
   gn_finalize_kernel<<<(unsigned)ceil_div((int64_t)total * 32, 256), 256, 0, st>>>(
-      reinterpret_cast<const float*>(ws), splits, (int)C, groups, rows_per_inst, eps, mean_rstd, total);
+      reinterpret_cast<const float*>(ws), splits, (int)C, groups, rows_per_inst, eps, gamma, beta, scale_shift, total);
   PB_LAUNCH_CHECK("gn_finalize_kernel");
   return PB_OK;
 }
 
 int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype,
                        int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
-                       int32_t groups, const float* mean_rstd, const float* gamma,
-                       const float* beta, int32_t silu, pb_stream_t stream) {
+                       const float* scale_shift, int32_t silu, pb_stream_t stream) {
   using namespace pb;
-  PB_REQUIRE(x && y && mean_rstd && gamma && beta, "pb_groupnorm_apply: null pointer");
-  PB_REQUIRE(n_inst > 0 && rows_per_inst > 0 && C > 0 && groups > 0, "pb_groupnorm_apply: empty input");
-  PB_REQUIRE(C % 4 == 0 && C % groups == 0 && ldx % 4 == 0 && ldy % 4 == 0,
-             "pb_groupnorm_apply: need C %% 4 == 0, C %% groups == 0, ld %% 4 == 0");
-  const int64_t total_vec = n_inst * rows_per_inst * (C / 4);
-  int64_t blocks = ceil_div(total_vec, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  PB_REQUIRE(x && y && scale_shift, "pb_groupnorm_apply: null pointer");
+  PB_REQUIRE(n_inst > 0 && n_inst <= 65535 && rows_per_inst > 0 && C > 0, "pb_groupnorm_apply: bad sizes");
+  PB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "pb_groupnorm_apply: need C %% 4 == 0, ld %% 4 == 0");
   cudaStream_t st = to_stream(stream);
-  PB_DISPATCH_DTYPE(x_dtype, TX, {
-    PB_DISPATCH_DTYPE(y_dtype, TY, {
-      gn_apply_kernel<TX, TY><<<(unsigned)blocks, 256, 0, st>>>(
-          reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<TY*>(y), ldy, rows_per_inst, (int)C,
-          groups, mean_rstd, gamma, beta, silu, total_vec);
+  int TX, TY;
+  gn_shape((int)(C / 4), &TX, &TY);
+  dim3 grid((unsigned)ceil_div(rows_per_inst, GN_APPLY_ROWS), (unsigned)n_inst);
+  PB_DISPATCH_DTYPE(x_dtype, TXT, {
+    PB_DISPATCH_DTYPE(y_dtype, TYT, {
+      gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const TXT*>(x), ldx,
+                                                             reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
+                                                             scale_shift, silu, TX, TY);
     })
   })
   PB_LAUNCH_CHECK("gn_apply_kernel");

@@ -58,8 +58,8 @@ SYMBOLS = {
     "pb_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "pb_tc_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "pb_groupnorm_ws_bytes": (_sz, [_i64, _i64, _i64]),
-    "pb_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _sz, _vp]),
-    "pb_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
+    "pb_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pb_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _i32, _vp]),
     "pb_layernorm": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _f, _vp]),
     "pb_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pb_tc_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
@@ -67,6 +67,7 @@ SYMBOLS = {
     "pb_silu": (C.c_int, [_vp, _vp, _i64, _vp]),
     "pb_add": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "pb_copy_rows": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
+    "pb_upsample2x_rows": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _vp]),
     "pb_timestep_embedding": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "pb_video_to_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i64, _i64, _i64, _vp]),
     "pb_rows_to_video": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp]),
@@ -77,6 +78,43 @@ SYMBOLS = {
 _lib = None
 _lock = threading.Lock()
 launches = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+# ---- optional per-launch timing (bench.py roofline / breakdown); off by default ----------------
+_prof = None
+
+
+def profile_begin():
+    """Start recording (name, algorithmic flops, algorithmic bytes, CUDA-event pair) per C-ABI call."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """Stop recording; returns [dict(name, ms, flops, bytes)] (synchronises the device once)."""
+    global _prof
+    items, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    return [dict(name=n, flops=f, bytes=b, ms=e0.elapsed_time(e1)) for (n, f, b, e0, e1) in items]
+
+
+def _tick(name, flops=0, nbytes=0):
+    if _prof is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return (name, flops, nbytes, e0)
+
+
+def _tock(tok):
+    if tok is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _prof.append(tok + (e1,))
+
+
+def _nbytes(*ts):
+    return sum(t.shape[0] * t.shape[1] * t.element_size() for t in ts if t is not None)
 
 
 def lib_path():
@@ -130,8 +168,14 @@ def _rows(t):
     return t.data_ptr(), t.stride(0)
 
 
+_tc = None
+
+
 def supports_tc():
-    return load().pb_device_supports_tc() == 1
+    global _tc
+    if _tc is None:
+        _tc = load().pb_device_supports_tc() == 1
+    return _tc
 
 
 def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=False,
@@ -167,10 +211,13 @@ def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=
         g.cin, g.frames, g.frame_rows = convt
     lib = load()
     fn = lib.pb_tc_gemm if tc else lib.pb_gemm
+    tok = _tick(("tc_" if tc else "simt_") + ("gemm", "conv3x3", "convt3")[mode] + ("_geglu" if geglu else ""),
+                2 * g.M * g.N * g.K, (g.M * g.K // (1, 9, 3)[mode] + g.N * g.K) * a.element_size() + _nbytes(c, residual))
     rc = fn(C.byref(g), _stream())
     if rc == E_UNSUPPORTED and tc:
         return False
     _check(rc, "pb_tc_gemm" if tc else "pb_gemm")
+    _tock(tok)
     launches += 1
     return True
 
@@ -181,16 +228,18 @@ def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32):
     lib = load()
     Cc = x.shape[1]
     ws_bytes = lib.pb_groupnorm_ws_bytes(n_inst, rows_per_inst, Cc)
-    ws = torch.empty(ws_bytes // 4 + n_inst * groups * 2, dtype=torch.float32, device=x.device)
+    ws = torch.empty(ws_bytes // 4 + n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
     stats = ws[ws_bytes // 4:]
     xp, ldx = _rows(x)
     yp, ldy = _rows(y)
     st = _stream()
-    _check(lib.pb_groupnorm_stats(xp, dt(x), ldx, n_inst, rows_per_inst, Cc, groups, eps,
-                                  stats.data_ptr(), ws.data_ptr(), ws_bytes, st), "pb_groupnorm_stats")
-    _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc, groups,
-                                  stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(silu), st),
-           "pb_groupnorm_apply")
+    tok = _tick("groupnorm", 0, 2 * _nbytes(x) + _nbytes(y))
+    _check(lib.pb_groupnorm_stats(xp, dt(x), ldx, n_inst, rows_per_inst, Cc, groups, eps, gamma.data_ptr(),
+                                  beta.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes, st),
+           "pb_groupnorm_stats")
+    _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc,
+                                  stats.data_ptr(), int(silu), st), "pb_groupnorm_apply")
+    _tock(tok)
     launches += 3
     return stats
 
@@ -199,8 +248,10 @@ def layernorm(x, y, gamma, beta, eps=1e-5):
     global launches
     xp, ldx = _rows(x)
     yp, ldy = _rows(y)
+    tok = _tick("layernorm", 0, _nbytes(x, y))
     _check(load().pb_layernorm(xp, dt(x), ldx, yp, dt(y), ldy, x.shape[0], x.shape[1],
                                gamma.data_ptr(), beta.data_ptr(), eps, _stream()), "pb_layernorm")
+    _tock(tok)
     launches += 1
 
 
@@ -222,10 +273,15 @@ def attention(q, k, v, out, o_addr, batch, heads, n_q, n_kv, scale, dtype, accum
     a.scale, a.dtype, a.accumulate = scale, dtype, int(accumulate)
     lib = load()
     fn = lib.pb_tc_attention if tc else lib.pb_attention
+    esz = 2 if dtype == BF16 else 4
+    kind = "temporal" if n_q <= 32 else ("self" if n_q == n_kv else "cross")
+    tok = _tick(("tc_" if tc else "simt_") + "attn_" + kind, 4 * batch * heads * n_q * n_kv * 64,
+                batch * heads * 64 * esz * (2 * n_q + 2 * n_kv))
     rc = fn(C.byref(a), _stream())
     if rc == E_UNSUPPORTED and tc:
         return False
     _check(rc, "pb_tc_attention" if tc else "pb_attention")
+    _tock(tok)
     launches += 1
     return True
 
@@ -234,7 +290,9 @@ def geglu(u, y):
     global launches
     up, ldu = _rows(u)
     yp, ldy = _rows(y)
+    tok = _tick("geglu", 0, _nbytes(u, y))
     _check(load().pb_geglu(up, dt(u), ldu, yp, dt(y), ldy, u.shape[0], y.shape[1], _stream()), "pb_geglu")
+    _tock(tok)
     launches += 1
 
 
@@ -254,8 +312,21 @@ def copy_rows(src, dst):
     global launches
     sp, lds = _rows(src)
     dp, ldd = _rows(dst)
+    tok = _tick("copy_rows", 0, _nbytes(src, dst))
     _check(load().pb_copy_rows(sp, dt(src), lds, dp, dt(dst), ldd, src.shape[0], src.shape[1], _stream()),
            "pb_copy_rows")
+    _tock(tok)
+    launches += 1
+
+
+def upsample2x_rows(src, dst, n_img, H, W):
+    global launches
+    sp, lds = _rows(src)
+    dp, ldd = _rows(dst)
+    tok = _tick("upsample2x", 0, _nbytes(src, dst))
+    _check(load().pb_upsample2x_rows(sp, dt(src), lds, dp, dt(dst), ldd, n_img, H, W, src.shape[1], _stream()),
+           "pb_upsample2x_rows")
+    _tock(tok)
     launches += 1
 
 

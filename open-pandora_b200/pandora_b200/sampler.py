@@ -75,6 +75,84 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
     return guidance_rescale * (noise_cfg * (std_text / std_cfg)) + (1 - guidance_rescale) * noise_cfg
 
 
+class GraphedCFGStep:
+    """One classifier-free-guidance DDIM step (video->rows, U-Net x2, fused update) captured ONCE as a
+    CUDA graph and replayed per step: ~2400 kernel launches collapse into one graph launch, and there
+    is no per-step host<->device scalar traffic (the step index lives on the device and the update
+    kernel advances it).  All buffers are static:
+
+        x        fp32 latent, updated in place by the replay
+        noise    fp32, refilled by the caller before each replay (same torch.randn stream as eager)
+        ts       int64 DDPM timestep of the step
+        pred_x0  fp32 output of the step
+
+    The conditioning (cross-attention context, c_concat) is read from the tensors given at construction;
+    `refresh_conditioning()` must be called after their contents change (it recomputes the cached K/V
+    projections in place so the captured graph sees them)."""
+
+    def __init__(self, sampler, unet, shape, cond, uncond, fs, cfg_scale, guidance_rescale, temperature, table):
+        dev = sampler.model.device
+        self.unet, self.sampler = unet, sampler
+        self.cfg = uncond is not None and cfg_scale != 1.0
+        self.cfg_scale, self.rescale, self.temperature = float(cfg_scale), float(guidance_rescale), float(temperature)
+        f32 = torch.float32
+        self.x = torch.zeros(shape, dtype=f32, device=dev)
+        self.noise = torch.zeros(shape, dtype=f32, device=dev)
+        self.pred_x0 = torch.zeros(shape, dtype=f32, device=dev)
+        self.ts = torch.zeros((shape[0],), dtype=torch.long, device=dev)
+        self.step_index = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.table = table.flip(0).contiguous()          # row i = i-th executed step (index S-1-i)
+        self.ws = torch.zeros(4 * shape[0], dtype=torch.float64, device=dev)
+        self.fs = fs
+        cat = lambda c: c[0] if len(c) == 1 else torch.cat(list(c), 1)
+        self.ctx_c, self.z_c = cat(cond["c_crossattn"]), cat(cond["c_concat"])
+        self.ctx_u = self.z_u = None
+        if self.cfg:
+            self.ctx_u, self.z_u = cat(uncond["c_crossattn"]), cat(uncond["c_concat"])
+        self.graph = None
+        self.launches_per_step = 0
+
+    def _body(self):
+        v_c = self.unet(self.x, self.ts, context=self.ctx_c, fs=self.fs, x_concat=[self.z_c])
+        v_u = self.unet(self.x, self.ts, context=self.ctx_u, fs=self.fs, x_concat=[self.z_u]) if self.cfg else None
+        abi.ddim_cfg_step(self.x, v_c, v_u, self.noise, self.x, self.pred_x0, self.cfg_scale, self.rescale,
+                          self.temperature, self.table, self.step_index, True, self.ws)
+
+    def capture(self):
+        # eager warm-up on a side stream (fills weight packs / context K,V caches, configures kernels)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        # the graph bakes raw pointers: pin the context K|V caches it reads
+        self._keep = list(self.unet._ctx_cache.values())
+        l0 = abi.launches
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches_per_step = abi.launches - l0
+        self.step_index.zero_()
+
+    def refresh_conditioning(self):
+        for ctx in (self.ctx_c, self.ctx_u):
+            if ctx is not None:
+                self.unet.refresh_context(ctx, self.x.shape[2])
+
+    def reset(self, x_T):
+        self.x.copy_(x_T)
+        self.step_index.zero_()
+
+    def step(self, ddpm_step, noise=None):
+        self.ts.fill_(int(ddpm_step))
+        # same call (shape, device) as the reference's noise_like -> identical generator consumption
+        self.noise.copy_(torch.randn(self.noise.shape, device=self.noise.device) if noise is None else noise)
+        self.graph.replay()
+        abi.launches += self.launches_per_step
+        return self.x, self.pred_x0
+
+
 class DDIMSampler(object):
     def __init__(self, model, schedule="linear", **kwargs):
         super().__init__()
@@ -83,6 +161,8 @@ class DDIMSampler(object):
         self.schedule = schedule
         self.counter = 0
         self._tables = {}
+        #: capture the CFG step as a CUDA graph when the native U-Net is underneath (set False to run eagerly)
+        self.use_cuda_graph = True
 
     def register_buffer(self, name, attr):
         if isinstance(attr, torch.Tensor) and attr.device != self.model.device:
@@ -221,8 +301,23 @@ class DDIMSampler(object):
             iterator = time_range
         clean_cond = kwargs.pop("clean_cond", False)
         pred_x0 = img
+        graphed = self._graphed_step(cond, unconditional_conditioning, shape, fs, unconditional_guidance_scale,
+                                     guidance_rescale, temperature, mask, noise_dropout, score_corrector,
+                                     quantize_denoised, ddim_use_original_steps, timesteps, kwargs)
+        if graphed is not None:
+            graphed.reset(img)
         for i, step in enumerate(iterator):
             index = total_steps - i - 1
+            if graphed is not None:
+                img, pred_x0 = graphed.step(step)
+                if callback:
+                    callback(i)
+                if img_callback:
+                    img_callback(pred_x0.to(out_dtype), i)
+                if index % log_every_t == 0 or index == total_steps - 1:
+                    intermediates["x_inter"].append(img.to(out_dtype, copy=True))
+                    intermediates["pred_x0"].append(pred_x0.to(out_dtype, copy=True))
+                continue
             ts = torch.full((b,), int(step), device=device, dtype=torch.long)
             if mask is not None:
                 assert x0 is not None
@@ -242,7 +337,26 @@ class DDIMSampler(object):
             if index % log_every_t == 0 or index == total_steps - 1:
                 intermediates["x_inter"].append(img.to(out_dtype))
                 intermediates["pred_x0"].append(pred_x0.to(out_dtype))
-        return img.to(out_dtype), intermediates
+        return img.to(out_dtype, copy=True), intermediates
+
+    def _graphed_step(self, cond, uc, shape, fs, cfg_scale, guidance_rescale, temperature, mask, noise_dropout,
+                      score_corrector, quantize_denoised, use_original_steps, timesteps, kwargs):
+        """A GraphedCFGStep for this call, or None when the generic eager path must be used."""
+        m = self.model
+        inner = getattr(m, "model", None)
+        unet = getattr(inner, "diffusion_model", None)
+        ok = (self.use_cuda_graph and isinstance(unet, UNetModel) and isinstance(cond, dict)
+              and getattr(inner, "conditioning_key", None) == "hybrid" and m.parameterization == "v"
+              and mask is None and noise_dropout == 0. and score_corrector is None and not quantize_denoised
+              and not use_original_steps and len(shape) == 5 and torch.device(m.device).type == "cuda"
+              and (uc is None or isinstance(uc, dict)) and isinstance(timesteps, np.ndarray)
+              and len(timesteps) == len(self.ddim_timesteps))
+        if not ok:
+            return None
+        table, _ = self._step_table(False)
+        g = GraphedCFGStep(self, unet, tuple(shape), cond, uc, fs, cfg_scale, guidance_rescale, temperature, table)
+        g.capture()
+        return g
 
     # --------------------------------------------------------------------------------- one step
     def _denoise(self, x, t, c, **kwargs):

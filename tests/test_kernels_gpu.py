@@ -215,6 +215,16 @@ def test_geglu_silu_add_copy(abi):
     assert torch.equal(dst[:, 100:356], u.bfloat16()) and float(dst[:, :100].abs().max()) == 0
 
 
+def test_upsample2x_rows(abi):
+    n, H, W, C = 3, 5, 6, 64
+    x = rnd(n, C, H, W, seed=44)
+    rows = x.permute(0, 2, 3, 1).reshape(n * H * W, C).contiguous()
+    out = torch.empty(n * 4 * H * W, C, dtype=torch.bfloat16, device="cuda")
+    abi.upsample2x_rows(rows, out, n, H, W)
+    ref = F.interpolate(x, scale_factor=2, mode="nearest").permute(0, 2, 3, 1).reshape(-1, C).bfloat16()
+    assert torch.equal(out, ref)
+
+
 def test_timestep_embedding_bf16_table(abi):
     half = 160
     freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.bfloat16) / half).float().cuda()

@@ -75,7 +75,7 @@ def test_tc_conv3x3(abi, n, cin, cout, H, W):
     assert ok, "expected the TMA path to take this shape"
     ref_rows = ref.permute(0, 2, 3, 1).reshape(n * H * W, cout) + res.double() \
         + emb.double().repeat_interleave(rb_rows, 0)
-    assert rel_l2(c, ref_rows) < 3e-6
+    assert rel_l2(c, ref_rows) < 1e-5      # K up to 23040 accumulated in the tensor core's fp32
 
 
 def test_tc_conv3x3_declines_what_it_cannot_tile(abi):
@@ -110,3 +110,51 @@ def test_tc_gemm_back_to_back_launches_are_deterministic(abi):
         abi.gemm(a, w, c, tc=True)
         outs.append(c)
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+# ------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,heads,nq,nk", [(2, 2, 128, 128), (3, 5, 160, 160), (2, 1, 640, 640), (1, 2, 2560, 2560),
+                                           (2, 3, 200, 77), (2, 2, 64, 16), (1, 1, 300, 129)])
+def test_tc_attention_frame_batched(abi, B, heads, nq, nk):
+    C = heads * 64
+    qkv = rnd(B * nq, 3 * C, seed=30, dtype=BF)
+    kv = rnd(B * nk, 2 * C, seed=31, dtype=BF)
+    q = qkv[:, :C].reshape(B, nq, C)
+    if nq == nk:
+        k, v = qkv[:, C:2 * C].reshape(B, nk, C), qkv[:, 2 * C:].reshape(B, nk, C)
+        kop = abi.operand(qkv, 1, nk * 3 * C, 0, 3 * C, C)
+        vop = abi.operand(qkv, 1, nk * 3 * C, 0, 3 * C, 2 * C)
+    else:
+        k, v = kv[:, :C].reshape(B, nk, C), kv[:, C:].reshape(B, nk, C)
+        kop = abi.operand(kv, 1, nk * 2 * C, 0, 2 * C, 0)
+        vop = abi.operand(kv, 1, nk * 2 * C, 0, 2 * C, C)
+    out = torch.full((B * nq, C), float("nan"), dtype=BF, device="cuda")
+    qop = abi.operand(qkv, 1, nq * 3 * C, 0, 3 * C, 0)
+    assert abi.attention(qop, kop, vop, out, (1, nq * C, 0, C), B, heads, nq, nk, 0.125, abi.BF16, tc=True)
+    ref = ref_attn(q, k, v, heads).reshape(B * nq, C)
+    e = rel_l2(out, ref)
+    assert e < 6e-3, e
+    assert abi.attention(qop, kop, vop, out, (1, nq * C, 0, C), B, heads, nq, nk, 0.125, abi.BF16, accumulate=True, tc=True)
+    assert rel_l2(out, 2 * ref) < 1e-2
+
+
+def test_tc_attention_text_kv_shared_across_frames(abi):
+    b, T, heads, nq, nk = 2, 4, 2, 160, 77
+    C = heads * 64
+    q = rnd(b * T * nq, C, seed=32, dtype=BF)
+    kv = rnd(b * nk, 2 * C, seed=33, dtype=BF)
+    out = torch.empty(b * T * nq, C, dtype=BF, device="cuda")
+    assert abi.attention(abi.operand(q, 1, nq * C, 0, C, 0), abi.operand(kv, T, nk * 2 * C, 0, 2 * C, 0),
+                         abi.operand(kv, T, nk * 2 * C, 0, 2 * C, C), out, (1, nq * C, 0, C), b * T, heads, nq, nk,
+                         0.125, abi.BF16, tc=True)
+    k = kv[:, :C].reshape(b, nk, C).repeat_interleave(T, 0)
+    v = kv[:, C:].reshape(b, nk, C).repeat_interleave(T, 0)
+    assert rel_l2(out, ref_attn(q.reshape(b * T, nq, C), k, v, heads).reshape(-1, C)) < 6e-3
+
+
+def test_tc_attention_declines_temporal_layout(abi):
+    qkv = rnd(16 * 24, 3 * 64, seed=34, dtype=BF)
+    out = torch.empty(16 * 24, 64, dtype=BF, device="cuda")
+    op = lambda off: abi.operand(qkv, 24, 16 * 24 * 192, 192, 24 * 192, off)
+    assert abi.attention(op(0), op(64), op(128), out, (24, 16 * 24 * 64, 64, 24 * 64), 24, 1, 16, 16, 0.125,
+                         abi.BF16, tc=True) is False

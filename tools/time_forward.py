@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--modes", default="bf16-tc,bf16-simt,fp32")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--compare", action="store_true")
+    ap.add_argument("--profile", action="store_true")
     a = ap.parse_args()
     latent = config.LATENT_512 if a.res == "512" else config.LATENT_1024
     t0 = time.time()
@@ -48,6 +49,18 @@ def main():
             e1.synchronize()
             ts.append(e0.elapsed_time(e1))
         outs[mode] = y.float()
+        if a.profile:
+            abi.profile_begin()
+            m(x, t, context=inp["context"])
+            agg = {}
+            for it in abi.profile_end():
+                g = agg.setdefault(it["name"], dict(n=0, ms=0.0, flops=0, bytes=0))
+                g["n"] += 1; g["ms"] += it["ms"]; g["flops"] += it["flops"]; g["bytes"] += it["bytes"]
+            tot = sum(g["ms"] for g in agg.values())
+            for k, g in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+                print(json.dumps(dict(mode=mode, kernel=k, n=g["n"], ms=round(g["ms"], 3), share=round(g["ms"] / tot, 3),
+                                      tflops=round(g["flops"] / g["ms"] / 1e9, 1), gbs=round(g["bytes"] / g["ms"] / 1e6, 1))))
+            print(json.dumps(dict(mode=mode, kernel="TOTAL(sum of launches)", ms=round(tot, 3))), flush=True)
         print(json.dumps(dict(mode=mode, res=a.res, ms=[round(v, 2) for v in ts], launches=nl,
                               finite=bool(torch.isfinite(y).all()),
                               mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))), flush=True)
