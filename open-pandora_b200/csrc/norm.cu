@@ -91,35 +91,48 @@ gn_partial_kernel(const T* __restrict__ x, int64_t ldx, int64_t R, int C, int sp
   }
 }
 
-// One warp per (instance, group): fold the partials in fp64 -> mean, rstd, then emit the per-channel
-// affine  y = x * scale + shift  (scale = rstd*gamma, shift = beta - mean*rstd*gamma).
-__global__ void gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64_t R, float eps,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ scale_shift /* [n_inst, 2, C] */, int total) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= total) return;
-  const int inst = warp / G, g = warp % G;
+// One 128-thread CTA per (instance, group): fold splits x C/G partials in fp64 -> mean, rstd, then emit
+// the per-channel affine  y = x * scale + shift  (scale = rstd*gamma, shift = beta - mean*rstd*gamma).
+// (The temporal blocks have a single instance with > 1000 splits: a one-warp fold was latency-bound.)
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64_t R, float eps,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ scale_shift /* [n_inst, 2, C] */) {
+  __shared__ double red[2][4];
+  __shared__ float stat[2];
+  const int inst = blockIdx.x / G, g = blockIdx.x % G;
   const int cpg = C / G;
+  const int per = cpg * 2;                       // contiguous floats per split for this group
+  const float* base = ws + (int64_t)inst * splits * C * 2 + (int64_t)g * per;
   double s = 0.0, q = 0.0;
-  const int n = splits * cpg;
-  for (int i = lane; i < n; i += 32) {
-    int sp = i / cpg, c = g * cpg + i % cpg;
-    const float* p = ws + (((int64_t)inst * splits + sp) * C + c) * 2;
-    s += (double)p[0]; q += (double)p[1];
+  const int n = splits * per;
+  for (int i = threadIdx.x; i < n; i += 128) {
+    const int sp = i / per, j = i - sp * per;
+    const float v = base[(int64_t)sp * C * 2 + j];
+    if (j & 1) q += (double)v; else s += (double)v;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
-  const double cnt = (double)R * cpg;
-  const double mean = s / cnt;
-  double var = q / cnt - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float meanf = (float)mean;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = s; red[1][w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double ss = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    const double qq = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    const double cnt = (double)R * cpg;
+    const double mean = ss / cnt;
+    double var = qq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[0] = (float)mean;
+    stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float meanf = stat[0], rstd = stat[1];
   float* sc = scale_shift + (int64_t)inst * 2 * C;
-  for (int i = lane; i < cpg; i += 32) {
+  for (int i = threadIdx.x; i < cpg; i += 128) {
     const int c = g * cpg + i;
     const float a = rstd * gamma[c];
     sc[c] = a;
@@ -234,9 +247,8 @@ int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_in
                                                       splits, TX, TY, reinterpret_cast<float*>(ws));
   })
   PB_LAUNCH_CHECK("gn_partial_kernel");
-  const int total = (int)(n_inst * groups);
-  gn_finalize_kernel<<<(unsigned)ceil_div((int64_t)total * 32, 256), 256, 0, st>>>(
-      reinterpret_cast<const float*>(ws), splits, (int)C, groups, rows_per_inst, eps, gamma, beta, scale_shift, total);
+  gn_finalize_kernel<<<(unsigned)(n_inst * groups), 128, 0, st>>>(
+      reinterpret_cast<const float*>(ws), splits, (int)C, groups, rows_per_inst, eps, gamma, beta, scale_shift);
   PB_LAUNCH_CHECK("gn_finalize_kernel");
   return PB_OK;
 }

@@ -154,6 +154,7 @@ def main():
     unet_case("small_b2ish", pcfg.small_unet(context_dim=64), (4, 16, 8, 16), True, 77, 8, 259, 15)
     sampler_case("s5_cfg75", small, pcfg.DIFFUSION_512, (4, 16, 8, 8), 5, 7.5, 0.0, 1234, 0, "uniform_trailing", 1.0)
     sampler_case("s8_cfg75_r07", small, pcfg.DIFFUSION_1024, (4, 16, 8, 8), 8, 7.5, 0.7, 1234, 1, "uniform_trailing", 1.0)
+    sampler_case("s50_cfg75_r07", small, pcfg.DIFFUSION_512, (4, 16, 8, 8), 50, 7.5, 0.7, 1234, 4, "uniform_trailing", 1.0)
     sampler_case("s4_eta0", small, pcfg.DIFFUSION_512, (4, 16, 8, 8), 4, 4.0, 0.0, 99, 2, "uniform_trailing", 0.0)
 
 

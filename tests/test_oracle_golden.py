@@ -12,7 +12,7 @@ from oracle import ddim_oracle, unet_oracle
 from pandora_b200.synthetic import synth_inputs, synth_state_dict
 
 UNET_CASES = ["unet_small_perframe", "unet_small_t499_nofs", "unet_small_sharedimg", "unet_small_b2ish"]
-DDIM_CASES = ["ddim_s5_cfg75", "ddim_s8_cfg75_r07", "ddim_s4_eta0"]
+DDIM_CASES = ["ddim_s5_cfg75", "ddim_s8_cfg75_r07", "ddim_s4_eta0", "ddim_s50_cfg75_r07"]
 
 
 def unet_case_inputs(meta):
