@@ -130,10 +130,13 @@ int validate_attn_args(const pb_attn_args* a, const char* who) {
 
 }  // namespace pb
 
+namespace pb { int launch_small_attention(const pb_attn_args* a, cudaStream_t st); }
+
 extern "C" int pb_attention(const pb_attn_args* a, pb_stream_t stream) {
   using namespace pb;
   int rc = validate_attn_args(a, "pb_attention");
   if (rc != PB_OK) return rc;
+  if (a->n_q == a->n_kv && a->n_q <= 16) return launch_small_attention(a, to_stream(stream));  // temporal
   AttnP p;
   p.q = {a->q.ptr, a->q.bdiv, a->q.bs_outer, a->q.bs_inner, a->q.rs};
   p.k = {a->k.ptr, a->k.bdiv, a->k.bs_outer, a->k.bs_inner, a->k.rs};

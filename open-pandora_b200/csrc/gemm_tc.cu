@@ -53,6 +53,7 @@ struct TcParams {
   int bw, bh, bn_img;    // CONV3X3: brick x, y, images ; CONVT3: bw = pixels, bh = frames
   int W, H;              // CONV3X3: image size ; CONVT3: W = HW (pixels per frame), H = T
   int tiles_x, tiles_y;  // CONV3X3: W/bw, H/bh ; CONVT3: HW/bw, T/bh
+  int cstride;           // CONV3X3 spatial stride (1 or 2); W/H above are OUTPUT sizes
 };
 
 template <int MODE>
@@ -127,7 +128,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
           } else if (MODE == PB_A_CONV3X3) {
             const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx + kx - 1, cy + ky - 1, cn);
+            tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx * p.cstride + kx - 1, cy * p.cstride + ky - 1, cn);
           } else {
             tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
           }
@@ -261,7 +262,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box) {
+                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -269,7 +270,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   }
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
-  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -388,20 +389,26 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
     uint64_t str[1] = {(uint64_t)a->lda * esz};
     uint32_t box[2] = {BLOCK_K, BLOCK_M};
-    rc = encode_tmap_bf16(&tmA, a->a, 2, dims, str, box);
+    rc = encode_tmap_bf16(&tmA, a->a, 2, dims, str, box, nullptr);
   } else if (a->a_mode == PB_A_CONV3X3) {
-    if (a->stride != 1 || a->upsample) TC_UNSUPPORTED("pb_tc_gemm: conv3x3 stride 2 / upsample not on the TMA path");
+    if (a->upsample) TC_UNSUPPORTED("pb_tc_gemm: upsample is folded only on the CUDA-core path (use pb_upsample2x_rows)");
     p.taps = 9;
-    const int W = a->in_w, H = a->in_h, n_img = (int)(a->M / ((int64_t)H * W));
-    p.W = W; p.H = H;
+    // bricks tile the OUTPUT image; for stride 2 the TMA box walks the input with element stride 2, so the
+    // strided gather is done by the copy engine (no im2col, no separate kernel)
+    const int s2 = a->stride;
+    const int W = a->out_w, H = a->out_h, n_img = (int)(a->M / ((int64_t)H * W));
+    p.W = W; p.H = H; p.cstride = s2;
     if (!pick_brick(W, H, n_img, &p.bw, &p.bh, &p.bn_img))
       TC_UNSUPPORTED("pb_tc_gemm: %dx%d x %d images has no exact 128-row brick", H, W, n_img);
+    if (s2 * p.bw > 256 || s2 * p.bh > 256) TC_UNSUPPORTED("pb_tc_gemm: strided box exceeds the TMA box limit");
     p.tiles_x = W / p.bw; p.tiles_y = H / p.bh;
     p.m_tiles = p.tiles_x * p.tiles_y * (n_img / p.bn_img);
-    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)W, (uint64_t)H, (uint64_t)n_img};
-    uint64_t str[3] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * W, (uint64_t)a->lda * esz * W * H};
-    uint32_t box[4] = {BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn_img};
-    rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box);
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)a->in_w, (uint64_t)a->in_h, (uint64_t)n_img};
+    uint64_t str[3] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * a->in_w,
+                       (uint64_t)a->lda * esz * a->in_w * a->in_h};
+    uint32_t box[4] = {BLOCK_K, (uint32_t)(s2 * p.bw), (uint32_t)(s2 * p.bh), (uint32_t)p.bn_img};
+    uint32_t est[4] = {1, (uint32_t)s2, (uint32_t)s2, 1};
+    rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box, s2 == 1 ? nullptr : est);
   } else {
     p.taps = 3;
     const int HW = a->frame_rows, T = a->frames, nb = (int)(a->M / ((int64_t)HW * T));
@@ -413,14 +420,14 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     uint64_t dims[4] = {(uint64_t)cin, (uint64_t)HW, (uint64_t)T, (uint64_t)nb};
     uint64_t str[3] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * HW, (uint64_t)a->lda * esz * HW * T};
     uint32_t box[4] = {BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, 1};
-    rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box);
+    rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box, nullptr);
   }
   if (rc != PB_OK) return rc;
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t str[1] = {(uint64_t)a->K * esz};
     uint32_t box[2] = {BLOCK_K, (uint32_t)(geglu ? p.block_n / 2 : p.block_n)};
-    rc = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box);
+    rc = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box, nullptr);
     if (rc != PB_OK) return rc;
   }
   const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;

@@ -1,0 +1,252 @@
+// groupnorm.cu — GroupNorm(32)(+SiLU) as HBM-streaming kernels.
+//
+// (basics.py:76-88; openaimodel3d.py:155,179,259-268,547; attention.py:265,331)
+//   rows layout [n_inst * R, C]; statistics per (instance, group) over R rows x C/G channels.
+//   Pass 1  gn_partial_kernel : grid (splits, n_inst); every thread owns one 4-channel vector column and walks
+//           rows with a fixed stride (4 loads in flight): coalesced, register accumulators; the CTA folds its
+//           channels into per-group (sum, sumsq) and writes [n_inst, splits, G, 2].
+//   Pass 2  gn_finalize_kernel: one CTA per (instance, group) folds the splits in fp64 -> mean, rstd ->
+//           per-channel (scale, shift).
+//   Pass 3  gn_apply_kernel   : y = x*scale + shift (+SiLU), vectorised, no integer division in the loop,
+//           written in the operand dtype the next GEMM wants (bf16 or fp32).
+#include "common.cuh"
+
+namespace pb {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_APPLY_ROWS = 64;   // rows per CTA in the apply pass
+
+// Thread mapping shared by both passes: TX threads across 4-channel vector columns, TY row lanes.
+// A thread keeps its column(s) for the whole CTA lifetime, so per-column data sits in registers and the
+// inner loops contain no integer division.
+static inline void gn_shape(int cv, int* TX, int* TY) {
+  *TX = cv < GN_THREADS ? cv : GN_THREADS;
+  *TY = GN_THREADS / *TX;
+}
+
+static inline int gn_splits(int64_t n_inst, int64_t R) {
+  // ~8 CTAs per SM overall, at least 8 rows per CTA
+  int64_t want = ceil_div(148 * 8, n_inst);
+  int64_t maxs = ceil_div(R, 8);
+  int64_t s = want < 1 ? 1 : want;
+  if (s > maxs) s = maxs;
+  if (s > 2048) s = 2048;
+  return (int)s;
+}
+
+constexpr int GN_MAX_C = 2560;
+
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_partial_kernel(const T* __restrict__ x, int64_t ldx, int64_t R, int C, int G, int splits, int TX, int TY,
+                  float* __restrict__ ws /* [n_inst, splits, G, 2] */) {
+  __shared__ float red[GN_THREADS * 8];
+  __shared__ float chan[GN_MAX_C * 2];           // per-channel (sum, sumsq) of this CTA's rows
+  const int inst = blockIdx.y, sp = blockIdx.x;
+  const int cv = C >> 2;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int64_t r_begin = R * sp / splits, r_end = R * (sp + 1) / splits;
+  const T* base = x + (int64_t)inst * R * ldx;
+  for (int v0 = 0; v0 < cv; v0 += TX) {
+    const int v = v0 + tx;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    if (v < cv && ty < TY) {
+      const T* col = base + (int64_t)v * 4;
+      int64_t r = r_begin + ty;
+      for (; r + 3 * TY < r_end; r += 4 * TY) {       // 4 independent loads in flight
+        float t0[4], t1[4], t2[4], t3[4];
+        load4(col + r * ldx, t0);
+        load4(col + (r + TY) * ldx, t1);
+        load4(col + (r + 2 * TY) * ldx, t2);
+        load4(col + (r + 3 * TY) * ldx, t3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s[i] += (t0[i] + t1[i]) + (t2[i] + t3[i]);
+          q[i] += (t0[i] * t0[i] + t1[i] * t1[i]) + (t2[i] * t2[i] + t3[i] * t3[i]);
+        }
+      }
+      for (; r < r_end; r += TY) {
+        float t[4];
+        load4(col + r * ldx, t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s[i] += t[i]; q[i] = fmaf(t[i], t[i], q[i]); }
+      }
+    }
+    if (TY > 1) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { red[threadIdx.x * 8 + i] = s[i]; red[threadIdx.x * 8 + 4 + i] = q[i]; }
+      __syncthreads();
+      if (ty == 0 && v < cv) {
+        for (int l = 1; l < TY; ++l) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { s[i] += red[(l * TX + tx) * 8 + i]; q[i] += red[(l * TX + tx) * 8 + 4 + i]; }
+        }
+      }
+    }
+    if (ty == 0 && v < cv) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { chan[(v * 4 + i) * 2] = s[i]; chan[(v * 4 + i) * 2 + 1] = q[i]; }
+    }
+  }
+  __syncthreads();
+  // channels -> groups (one thread per (group, stat))
+  if (threadIdx.x < 2 * G) {
+    const int g = threadIdx.x >> 1, st = threadIdx.x & 1, cpg = C / G;
+    float a = 0.f;
+    for (int c = 0; c < cpg; ++c) a += chan[(g * cpg + c) * 2 + st];
+    ws[(((int64_t)inst * splits + sp) * G + g) * 2 + st] = a;
+  }
+}
+
+// One 128-thread CTA per (instance, group): fold the splits in fp64 -> mean, rstd, then emit the per-channel
+// affine  y = x * scale + shift  (scale = rstd*gamma, shift = beta - mean*rstd*gamma).
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64_t R, float eps,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ scale_shift /* [n_inst, 2, C] */) {
+  __shared__ double red[2][4];
+  __shared__ float stat[2];
+  const int inst = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  const float* base = ws + ((int64_t)inst * splits * G + g) * 2;
+  double s = 0.0, q = 0.0;
+  for (int sp = threadIdx.x; sp < splits; sp += 128) {
+    const float2 v = *reinterpret_cast<const float2*>(base + (int64_t)sp * G * 2);
+    s += (double)v.x; q += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = s; red[1][w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double ss = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    const double qq = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    const double cnt = (double)R * cpg;
+    const double mean = ss / cnt;
+    double var = qq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[0] = (float)mean;
+    stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float meanf = stat[0], rstd = stat[1];
+  float* sc = scale_shift + (int64_t)inst * 2 * C;
+  for (int i = threadIdx.x; i < cpg; i += 128) {
+    const int c = g * cpg + i;
+    const float a = rstd * gamma[c];
+    sc[c] = a;
+    sc[C + c] = beta[c] - meanf * a;
+  }
+}
+
+template <typename TX_, typename TY_>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int64_t R, int C,
+                const float* __restrict__ scale_shift, int silu, int TX, int TY) {
+  const int inst = blockIdx.y;
+  const int cv = C >> 2;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  if (ty >= TY) return;
+  const int64_t r_begin = (int64_t)blockIdx.x * GN_APPLY_ROWS;
+  const int64_t r_end = r_begin + GN_APPLY_ROWS < R ? r_begin + GN_APPLY_ROWS : R;
+  const float* sc = scale_shift + (int64_t)inst * 2 * C;
+  const TX_* xb = x + (int64_t)inst * R * ldx;
+  TY_* yb = y + (int64_t)inst * R * ldy;
+  for (int v = tx; v < cv; v += TX) {
+    float a[4], b[4];
+    load4(sc + v * 4, a);
+    load4(sc + C + v * 4, b);
+    int64_t r = r_begin + ty;
+    for (; r + 3 * TY < r_end; r += 4 * TY) {         // 4 independent 16-byte loads in flight per thread
+      float t[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load4(xb + (r + u * TY) * ldx + (int64_t)v * 4, t[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float y0 = fmaf(t[u][j], a[j], b[j]);
+          o[j] = silu ? silu_f(y0) : y0;
+        }
+        store4(yb + (r + u * TY) * ldy + (int64_t)v * 4, o);
+      }
+    }
+    for (; r < r_end; r += TY) {
+      float t[4], o[4];
+      load4(xb + r * ldx + (int64_t)v * 4, t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float u = fmaf(t[j], a[j], b[j]);
+        o[j] = silu ? silu_f(u) : u;
+      }
+      store4(yb + r * ldy + (int64_t)v * 4, o);
+    }
+  }
+}
+
+}  // namespace pb
+
+extern "C" {
+
+size_t pb_groupnorm_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int64_t C) {
+  if (n_inst <= 0 || rows_per_inst <= 0 || C <= 0) return 0;
+  return (size_t)n_inst * pb::gn_splits(n_inst, rows_per_inst) * 32 * 2 * sizeof(float);
+}
+
+int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_inst,
+                       int64_t rows_per_inst, int64_t C, int32_t groups, float eps, const float* gamma,
+                       const float* beta, float* scale_shift, void* ws, size_t ws_bytes, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(x && scale_shift && ws && gamma && beta, "pb_groupnorm_stats: null pointer");
+  PB_REQUIRE(n_inst > 0 && rows_per_inst > 0 && C > 0 && groups > 0, "pb_groupnorm_stats: empty input");
+  PB_REQUIRE(C % 4 == 0 && C % groups == 0 && ldx % 4 == 0,
+             "pb_groupnorm_stats: need C %% 4 == 0, C %% groups == 0, ldx %% 4 == 0 (C=%lld)", (long long)C);
+  PB_REQUIRE(n_inst <= 65535, "pb_groupnorm_stats: n_inst too large");
+  PB_REQUIRE(C <= GN_MAX_C && groups <= 32, "pb_groupnorm_stats: C <= %d and groups <= 32 supported", GN_MAX_C);
+  const int splits = gn_splits(n_inst, rows_per_inst);
+  PB_REQUIRE(ws_bytes >= pb_groupnorm_ws_bytes(n_inst, rows_per_inst, C),
+             "pb_groupnorm_stats: workspace too small");
+  cudaStream_t st = to_stream(stream);
+  int TX, TY;
+  gn_shape((int)(C / 4), &TX, &TY);
+  dim3 grid(splits, (unsigned)n_inst);
+  PB_DISPATCH_DTYPE(x_dtype, T, {
+    gn_partial_kernel<T><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const T*>(x), ldx, rows_per_inst, (int)C,
+                                                      groups, splits, TX, TY, reinterpret_cast<float*>(ws));
+  })
+  PB_LAUNCH_CHECK("gn_partial_kernel");
+  gn_finalize_kernel<<<(unsigned)(n_inst * groups), 128, 0, st>>>(
+      reinterpret_cast<const float*>(ws), splits, (int)C, groups, rows_per_inst, eps, gamma, beta, scale_shift);
+  PB_LAUNCH_CHECK("gn_finalize_kernel");
+  return PB_OK;
+}
+
+int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype,
+                       int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
+                       const float* scale_shift, int32_t silu, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(x && y && scale_shift, "pb_groupnorm_apply: null pointer");
+  PB_REQUIRE(n_inst > 0 && n_inst <= 65535 && rows_per_inst > 0 && C > 0, "pb_groupnorm_apply: bad sizes");
+  PB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "pb_groupnorm_apply: need C %% 4 == 0, ld %% 4 == 0");
+  cudaStream_t st = to_stream(stream);
+  int TX, TY;
+  gn_shape((int)(C / 4), &TX, &TY);
+  dim3 grid((unsigned)ceil_div(rows_per_inst, GN_APPLY_ROWS), (unsigned)n_inst);
+  PB_DISPATCH_DTYPE(x_dtype, TXT, {
+    PB_DISPATCH_DTYPE(y_dtype, TYT, {
+      gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const TXT*>(x), ldx,
+                                                             reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
+                                                             scale_shift, silu, TX, TY);
+    })
+  })
+  PB_LAUNCH_CHECK("gn_apply_kernel");
+  return PB_OK;
+}
+
+}  // extern "C"

@@ -163,7 +163,7 @@ __device__ __forceinline__ bool elect_one() {
 // bf16 tensor, innermost dimension contiguous, 128-byte swizzle, zero fill out of bounds.
 // dims/box: rank entries, innermost first; strides_bytes: rank-1 entries (dims 1..rank-1).
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box);
+                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 }  // namespace tc
 }  // namespace pb

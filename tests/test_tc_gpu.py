@@ -83,7 +83,7 @@ def test_tc_conv3x3_declines_what_it_cannot_tile(abi):
     w = rnd(64, 9 * 64, seed=17, dtype=BF)
     c = torch.empty(64, 64, device="cuda")
     assert abi.gemm(rows, w, c, mode=abi.A_CONV3X3, conv=(64, 2, 2, 2, 2, 1, 0), tc=True) is False
-    assert abi.gemm(rows, w, c[:16], mode=abi.A_CONV3X3, conv=(64, 2, 2, 1, 1, 2, 0), tc=True, M=16) is False
+    assert abi.gemm(rows, w, c, mode=abi.A_CONV3X3, conv=(64, 2, 2, 4, 4, 1, 1), tc=True, M=256) is False
 
 
 @pytest.mark.parametrize("b,T,HW,C", [(1, 16, 160, 320), (2, 16, 64, 64), (1, 16, 40, 1280), (1, 16, 2560, 64),
@@ -158,3 +158,18 @@ def test_tc_attention_declines_temporal_layout(abi):
     op = lambda off: abi.operand(qkv, 24, 16 * 24 * 192, 192, 24 * 192, off)
     assert abi.attention(op(0), op(64), op(128), out, (24, 16 * 24 * 64, 64, 24 * 64), 24, 1, 16, 16, 0.125,
                          abi.BF16, tc=True) is False
+
+
+@pytest.mark.parametrize("n,cin,cout,H,W", [(16, 64, 64, 8, 16), (2, 320, 320, 40, 64), (16, 640, 640, 20, 32),
+                                            (16, 1280, 1280, 10, 16), (4, 64, 64, 36, 64)])
+def test_tc_conv3x3_stride2_by_tma_element_strides(abi, n, cin, cout, H, W):
+    x = rnd(n, cin, H, W, seed=41, dtype=BF)
+    w = rnd(cout, cin, 3, 3, seed=42, dtype=BF, scale=(9 * cin) ** -0.5)
+    bias = rnd(cout, seed=43)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), stride=2, padding=1)
+    oh, ow = ref.shape[-2:]
+    rows = x.permute(0, 2, 3, 1).reshape(n * H * W, cin).contiguous()
+    c = torch.full((n * oh * ow, cout), float("nan"), device="cuda")
+    ok = abi.gemm(rows, conv_weight_rows(w), c, bias=bias, mode=abi.A_CONV3X3, conv=(cin, H, W, oh, ow, 2, 0), tc=True)
+    assert ok
+    assert rel_l2(c, ref.permute(0, 2, 3, 1).reshape(n * oh * ow, cout)) < 1e-5
