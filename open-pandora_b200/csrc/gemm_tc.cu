@@ -7,8 +7,9 @@
 //                                into a ring of 128B-swizzled shared-memory stages (mbarrier full/empty)
 //   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (M=128, N=block_n, K=16) x4 per
 //                                stage; tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2..5  epilogue       : tcgen05.ld the 128 x block_n fp32 accumulator (each thread owns one row),
-//                                fuse bias / timestep-embedding row bias / residual / GEGLU, convert and store
+//   warps 2..5  epilogue       : tcgen05.ld the 128 x block_n fp32 accumulator in 32-column chunks (thread =
+//                                row), + bias / GEGLU, transpose through a padded shared-memory stage, then
+//                                row-contiguous (coalesced) row-bias / residual loads and stores
 // The accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the
 // MMAs of tile i+1.
 //
@@ -33,7 +34,12 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 220 * 1024;
+constexpr int EPI_CHUNK = 32;                           // accumulator columns per epilogue chunk
+constexpr int EPI_LD = EPI_CHUNK + 4;                   // padded row (floats): conflict-free v4 access
+constexpr int EPI_STAGE_BYTES = BLOCK_M * EPI_LD * 4;   // 18 KiB, x2 buffers
+constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 4) + 16;
+constexpr int SMEM_TOTAL = 227 * 1024;
+constexpr int SMEM_PIPE_BUDGET = SMEM_TOTAL - 1024 - 2 * EPI_STAGE_BYTES - BAR_BYTES;
 
 struct TcParams {
   void* c;
@@ -69,6 +75,8 @@ __device__ __forceinline__ int64_t out_row(const TcParams& p, int m_tile, int r)
   return ((int64_t)(tn * p.bn_img + bi) * p.H + (ty * p.bh + by)) * p.W + (tx * p.bw + bx);
 }
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int MODE, bool GEGLU, typename TC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -77,7 +85,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_stage_bytes = p.block_n * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  const uint32_t bar_base = smem_base + p.stages * stage_bytes;
+  const uint32_t epi_base = smem_base + p.stages * stage_bytes;          // 2 x [128][EPI_LD] fp32
+  const uint32_t bar_base = epi_base + 2 * EPI_STAGE_BYTES;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -174,68 +183,94 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ================================================================== epilogue (warps 2..5)
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
-    const int r = quarter * 32 + lane;       // accumulator row owned by this thread
+    const int r = quarter * 32 + lane;       // accumulator row owned by this thread in phase A
+    const int et = threadIdx.x - 64;         // 0..127
+    const int b_row0 = et >> 3;              // phase B: rows b_row0 + 16*i, 4 columns at b_col
+    const int b_col = (et & 7) * 4;
     TC* C = reinterpret_cast<TC*>(p.c);
     int acc = 0, acc_phase = 0;
+    uint32_t chunk_counter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
-      const int64_t m = out_row<MODE>(p, m_tile, r);
-      const bool row_ok = m < p.M;
+      // rows this thread stores in phase B (fixed for the tile)
+      int64_t rows_m[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = out_row<MODE>(p, m_tile, b_row0 + 16 * i);
+        rows_m[i] = m < p.M ? m : -1;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
       const int out_cols = GEGLU ? (p.block_n >> 1) : p.block_n;
       const int64_t n0 = (int64_t)n_tile * out_cols;       // first output column of the tile
-      const float* rb = (p.epi & PB_EPI_ROWBIAS) && row_ok ? p.rowbias + (m / p.rb_rows) * p.ldrb : nullptr;
-      const float* rs = (p.epi & PB_EPI_RESIDUAL) && row_ok ? p.residual + m * p.ldr : nullptr;
-      for (int c0 = 0; c0 < out_cols; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_row + (uint32_t)c0, v);
-        float g[16];
-        if (GEGLU) tmem_ld16(t_row + (uint32_t)(out_cols + c0), g);
-        tmem_ld_wait();
-        if (p.epi & PB_EPI_BIAS) {
+      for (int c0 = 0; c0 < out_cols; c0 += EPI_CHUNK) {
+        const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;   // 16 or 32
+        const uint32_t buf = epi_base + (chunk_counter & 1u) * EPI_STAGE_BYTES;
+        ++chunk_counter;
+        // ---- phase A: TMEM -> registers (+bias, GEGLU) -> padded smem stage, thread = row
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        for (int h = 0; h < EPI_CHUNK; h += 16) {
+          if (h < cw) {
+            float v[16];
+            tmem_ld16(t_row + (uint32_t)(c0 + h), v);
+            float g[16];
+            if (GEGLU) tmem_ld16(t_row + (uint32_t)(out_cols + c0 + h), g);
+            tmem_ld_wait();
+            if (p.epi & PB_EPI_BIAS) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + h + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                if (GEGLU) {
+                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_half + n0 + c0 + h + j));
+                  g[j] += g4.x; g[j + 1] += g4.y; g[j + 2] += g4.z; g[j + 3] += g4.w;
+                }
+              }
+            }
             if (GEGLU) {
-              float4 g4 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_half + n0 + c0 + j));
-              g[j] += g4.x; g[j + 1] += g4.y; g[j + 2] += g4.z; g[j + 3] += g4.w;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= gelu_f(g[j]);
             }
+            const uint32_t dst = buf + (uint32_t)(r * EPI_LD + h) * 4u;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 4u * j), "f"(v[j]), "f"(v[j + 1]),
+                           "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
           }
         }
-        if (GEGLU) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= gelu_f(g[j]);
+        if (c0 + EPI_CHUNK >= out_cols) {
+          // last chunk read: the accumulator buffer is drained, hand it back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (row_ok) {
-          if (rb) {
+        epi_bar_sync();   // stage written by all 128 epilogue threads (also orders reuse of the other buffer)
+        // ---- phase B: row-contiguous: 8 lanes x 16 B cover one 128-byte row segment
+        if (b_col < cw) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 t4 = __ldg(reinterpret_cast<const float4*>(rb + n0 + c0 + j));
-              v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+          for (int i = 0; i < 8; ++i) {
+            const int64_t m = rows_m[i];
+            if (m < 0) continue;
+            float4 val;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w)
+                         : "r"(buf + (uint32_t)((b_row0 + 16 * i) * EPI_LD + b_col) * 4u));
+            const int64_t n = n0 + c0 + b_col;
+            if (p.epi & PB_EPI_ROWBIAS) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.rowbias + (m / p.rb_rows) * p.ldrb + n));
+              val.x += t4.x; val.y += t4.y; val.z += t4.z; val.w += t4.w;
             }
-          }
-          if (rs) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              float4 t4 = *reinterpret_cast<const float4*>(rs + n0 + c0 + j);
-              v[j] += t4.x; v[j + 1] += t4.y; v[j + 2] += t4.z; v[j + 3] += t4.w;
+            if (p.epi & PB_EPI_RESIDUAL) {
+              const float4 t4 = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n);
+              val.x += t4.x; val.y += t4.y; val.z += t4.z; val.w += t4.w;
             }
-          }
-          TC* dst = C + m * p.ldc + n0 + c0;
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-            store4(dst + j, o);
+            const float o[4] = {val.x, val.y, val.z, val.w};
+            store4(C + m * p.ldc + n, o);
           }
         }
       }
-      // accumulator buffer drained: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -324,7 +359,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
   static bool configured = false;
   auto kern = tc_gemm_kernel<MODE, GEGLU, TC>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
     configured = true;
   }
@@ -431,9 +466,9 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     if (rc != PB_OK) return rc;
   }
   const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
-  p.stages = SMEM_BUDGET / stage_bytes;
+  p.stages = SMEM_PIPE_BUDGET / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 8 * (2 * MAX_STAGES + 4) + 16;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 2 * EPI_STAGE_BYTES + BAR_BYTES;
 
   cudaStream_t st = to_stream(stream);
   const int cd = a->c_dtype;
