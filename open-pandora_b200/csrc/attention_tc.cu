@@ -70,6 +70,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// MUFU ex2 (approximate, flush-to-zero): ~2 ulp, the standard flash-attention choice
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -174,7 +181,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     auto fold_o = [&](int t, float m_t) {
       mbar_wait(o_full(t & 1), (t >> 1) & 1);
       tc_fence_after();
-      const float corr = exp2f(m_acc - m_t);   // 0 on the first tile (m_acc = -inf)
+      const float corr = fast_exp2(m_acc - m_t);   // 0 on the first tile (m_acc = -inf)
       m_acc = m_t;
 #pragma unroll
       for (int c = 0; c < ATT_D; c += 32) {
@@ -193,31 +200,52 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(s_full(b), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = lane_addr + S_COL0 + (uint32_t)b * ATT_BN;
+      const bool full = valid >= ATT_BN;          // no key masking needed (all but the last tile)
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < ATT_BN; c += 32) {
-        float v[32];
-        tmem_ld32(s_addr + c, v);
+      for (int c = 0; c < ATT_BN; c += 64) {
+        float v0[32], v1[32];
+        tmem_ld32(s_addr + c, v0);
+        tmem_ld32(s_addr + c + 32, v1);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < valid) ? v[i] : -INFINITY);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(v0[i], v1[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            mx = fmaxf(mx, (c + i < valid) ? v0[i] : -INFINITY);
+            mx = fmaxf(mx, (c + 32 + i < valid) ? v1[i] : -INFINITY);
+          }
+        }
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      l *= exp2f(m_run - m_new);
+      l *= fast_exp2(m_run - m_new);
       m_run = m_new;
       const uint32_t p_row = sP(b) + (uint32_t)r * 128;
+      float lsum = 0.f;
 #pragma unroll
       for (int c = 0; c < ATT_BN; c += 32) {
         float v[32];
         tmem_ld32(s_addr + c, v);
         tmem_ld_wait();
         uint32_t w[16];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = (c + i < valid) ? exp2f(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
-          const float p1 = (c + i + 1 < valid) ? exp2f(fmaf(v[i + 1], p.scale_log2, -m_new)) : 0.f;
-          l += p0 + p1;
-          w[i >> 1] = pack_bf16(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(fmaf(v[i], p.scale_log2, -m_new));
+            const float p1 = fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new));
+            lsum += p0 + p1;
+            w[i >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c + i < valid) ? fast_exp2(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
+            const float p1 = (c + i + 1 < valid) ? fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new)) : 0.f;
+            lsum += p0 + p1;
+            w[i >> 1] = pack_bf16(p0, p1);
+          }
         }
         // 32 keys = 64 B = 4 chunks of 16 B; K-block (c / 64), chunk index within the 128-byte row
         const uint32_t blk = p_row + (uint32_t)(c >> 6) * TILE_BYTES;
@@ -230,6 +258,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                        : "memory");
         }
       }
+      l += lsum;
       fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full(b));

@@ -199,15 +199,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t m = out_row<MODE>(p, m_tile, b_row0 + 16 * i);
         rows_m[i] = m < p.M ? m : -1;
       }
+      const int out_cols = GEGLU ? (p.block_n >> 1) : p.block_n;
+      const int64_t n0 = (int64_t)n_tile * out_cols;       // first output column of the tile
+      // residual + row-bias of a chunk are fetched one chunk ahead (registers), so their L2/HBM latency hides
+      // behind the TMEM drain and the barrier instead of being exposed after it
+      const bool has_add = (p.epi & (PB_EPI_RESIDUAL | PB_EPI_ROWBIAS)) != 0;
+      float4 add_cur[8], add_nxt[8];
+      auto fetch_add = [&](int c0, float4 (&dst)[8]) {
+        const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int64_t m = rows_m[i];
+          if (m >= 0 && b_col < cw) {
+            const int64_t n = n0 + c0 + b_col;
+            if (p.epi & PB_EPI_RESIDUAL) t = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n);
+            if (p.epi & PB_EPI_ROWBIAS) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(p.rowbias + (m / p.rb_rows) * p.ldrb + n));
+              t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+          }
+          dst[i] = t;
+        }
+      };
+      if (has_add) fetch_add(0, add_cur);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-      const int out_cols = GEGLU ? (p.block_n >> 1) : p.block_n;
-      const int64_t n0 = (int64_t)n_tile * out_cols;       // first output column of the tile
       for (int c0 = 0; c0 < out_cols; c0 += EPI_CHUNK) {
         const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;   // 16 or 32
         const uint32_t buf = epi_base + (chunk_counter & 1u) * EPI_STAGE_BYTES;
         ++chunk_counter;
+        if (has_add && c0 + EPI_CHUNK < out_cols) fetch_add(c0 + EPI_CHUNK, add_nxt);
         // ---- phase A: TMEM -> registers (+bias, GEGLU) -> padded smem stage, thread = row
 #pragma unroll
         for (int h = 0; h < EPI_CHUNK; h += 16) {
@@ -257,18 +280,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w)
                          : "r"(buf + (uint32_t)((b_row0 + 16 * i) * EPI_LD + b_col) * 4u));
-            const int64_t n = n0 + c0 + b_col;
-            if (p.epi & PB_EPI_ROWBIAS) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.rowbias + (m / p.rb_rows) * p.ldrb + n));
-              val.x += t4.x; val.y += t4.y; val.z += t4.z; val.w += t4.w;
-            }
-            if (p.epi & PB_EPI_RESIDUAL) {
-              const float4 t4 = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n);
-              val.x += t4.x; val.y += t4.y; val.z += t4.z; val.w += t4.w;
-            }
+            if (has_add) { val.x += add_cur[i].x; val.y += add_cur[i].y; val.z += add_cur[i].z; val.w += add_cur[i].w; }
             const float o[4] = {val.x, val.y, val.z, val.w};
-            store4(C + m * p.ldc + n, o);
+            store4(C + m * p.ldc + n0 + c0 + b_col, o);
           }
+        }
+        if (has_add) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) add_cur[i] = add_nxt[i];
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -14,7 +14,7 @@
 namespace pb {
 
 constexpr int GN_THREADS = 256;
-constexpr int GN_APPLY_ROWS = 64;   // rows per CTA in the apply pass
+// apply pass: rows per CTA = 8 * TY (each thread streams 8 rows of its column, 4 loads in flight)
 
 // Thread mapping shared by both passes: TX threads across 4-channel vector columns, TY row lanes.
 // A thread keeps its column(s) for the whole CTA lifetime, so per-column data sits in registers and the
@@ -147,13 +147,13 @@ gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64
 template <typename TX_, typename TY_>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int64_t R, int C,
-                const float* __restrict__ scale_shift, int silu, int TX, int TY) {
+                const float* __restrict__ scale_shift, int silu, int TX, int TY, int rows_per_cta) {
   const int inst = blockIdx.y;
   const int cv = C >> 2;
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   if (ty >= TY) return;
-  const int64_t r_begin = (int64_t)blockIdx.x * GN_APPLY_ROWS;
-  const int64_t r_end = r_begin + GN_APPLY_ROWS < R ? r_begin + GN_APPLY_ROWS : R;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r_end = r_begin + rows_per_cta < R ? r_begin + rows_per_cta : R;
   const float* sc = scale_shift + (int64_t)inst * 2 * C;
   const TX_* xb = x + (int64_t)inst * R * ldx;
   TY_* yb = y + (int64_t)inst * R * ldy;
@@ -237,12 +237,13 @@ int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int
   cudaStream_t st = to_stream(stream);
   int TX, TY;
   gn_shape((int)(C / 4), &TX, &TY);
-  dim3 grid((unsigned)ceil_div(rows_per_inst, GN_APPLY_ROWS), (unsigned)n_inst);
+  const int rows_per_cta = 8 * TY;
+  dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
   PB_DISPATCH_DTYPE(x_dtype, TXT, {
     PB_DISPATCH_DTYPE(y_dtype, TYT, {
       gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const TXT*>(x), ldx,
                                                              reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
-                                                             scale_shift, silu, TX, TY);
+                                                             scale_shift, silu, TX, TY, rows_per_cta);
     })
   })
   PB_LAUNCH_CHECK("gn_apply_kernel");

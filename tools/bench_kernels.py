@@ -38,7 +38,7 @@ def timeit(fn, reps, flush=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--res", default="512")
-    ap.add_argument("--what", default="gemm,geglu,conv,convt")
+    ap.add_argument("--what", default="gemm,geglu,conv,convt,attn,norm")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--simt", action="store_true")
     ap.add_argument("--out", default=None)
@@ -78,6 +78,32 @@ def main():
             x, w, c = rn(M, C), rn(C, 3 * C), torch.empty(M, C, device=dev)
             t = timeit(lambda: abi.gemm(x, w, c, mode=abi.A_CONVT3, convt=(C, 16, hw), tc=tc), a.reps, flush)
             rows.append(dict(kind="convt3", C=C, HW=hw, ms=t * 1e3, tflops=2 * M * C * 3 * C / t / 1e12))
+    if "attn" in what:
+        for i, C in enumerate([320, 640, 1280]):
+            n, heads = (H >> i) * (W >> i), C // 64
+            qkv = rn(16 * n, 3 * C)
+            out = torch.empty(16 * n, C, device=dev, dtype=BF)
+            ld = 3 * C
+            op = lambda off: abi.operand(qkv, 1, n * ld, 0, ld, off)
+            t = timeit(lambda: abi.attention(op(0), op(C), op(2 * C), out, (1, n * C, 0, C), 16, heads, n, n, 0.125,
+                                             abi.BF16, tc=tc), a.reps, flush)
+            rows.append(dict(kind="attn_self", n=n, heads=heads, ms=t * 1e3, tflops=4 * 16 * heads * n * n * 64 / t / 1e12))
+            kv = rn(77, 2 * C)
+            t = timeit(lambda: abi.attention(op(0), abi.operand(kv, 16, 77 * 2 * C, 0, 2 * C, 0),
+                                             abi.operand(kv, 16, 77 * 2 * C, 0, 2 * C, C), out, (1, n * C, 0, C), 16, heads,
+                                             n, 77, 0.125, abi.BF16, tc=tc), a.reps, flush)
+            rows.append(dict(kind="attn_cross77", n=n, heads=heads, ms=t * 1e3, tflops=4 * 16 * heads * n * 77 * 64 / t / 1e12))
+    if "norm" in what:
+        for i, C in enumerate([320, 640, 1280, 1280]):
+            hw = (H >> i) * (W >> i)
+            x = torch.randn(16 * hw, C, device=dev)
+            y = torch.empty(16 * hw, C, device=dev, dtype=BF)
+            gmm, bt = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+            for n_inst, tag in ((16, "frame"), (1, "clip")):
+                t = timeit(lambda: abi.groupnorm(x, y, n_inst, 16 * hw // n_inst, gmm, bt, 1e-5, True), a.reps, flush)
+                rows.append(dict(kind="groupnorm_" + tag, C=C, rows=16 * hw, ms=t * 1e3, gbs=(2 * x.numel() * 4 + y.numel() * 2) / t / 1e9))
+            t = timeit(lambda: abi.layernorm(x, y, gmm, bt), a.reps, flush)
+            rows.append(dict(kind="layernorm", C=C, rows=16 * hw, ms=t * 1e3, gbs=(x.numel() * 4 + y.numel() * 2) / t / 1e9))
     for r in rows:
         print(json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()}))
     if a.out:
