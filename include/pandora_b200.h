@@ -115,6 +115,17 @@ int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int
                        int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
                        const float* scale_shift, int32_t silu, pb_stream_t stream);
 
+/* Sequence-parallel split of pb_groupnorm_stats (temporal blocks normalise over ALL frames and pixels of a
+ * clip, openaimodel3d.py:259, attention.py:331,368, while a rank holds a slice): pb_groupnorm_sums writes this
+ * rank's fp64 (sum, sumsq) per (instance, group); the caller all-reduces them; pb_groupnorm_affine turns the
+ * global sums (count = global elements per group) into scale_shift for pb_groupnorm_apply.          */
+int pb_groupnorm_sums(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_inst, int64_t rows_per_inst,
+                      int64_t C, int32_t groups, double* sums /* [n_inst, groups, 2] */, void* ws,
+                      size_t ws_bytes, pb_stream_t stream);
+int pb_groupnorm_affine(const double* sums, int64_t n_inst, int64_t C, int32_t groups, double count,
+                        float eps, const float* gamma, const float* beta, float* scale_shift,
+                        pb_stream_t stream);
+
 /* ---- LayerNorm ---------------------------------------------------------------------------------
  * Replaces nn.LayerNorm(dim) eps 1e-5 at attention.py:225-227,243-245.                            */
 int pb_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,

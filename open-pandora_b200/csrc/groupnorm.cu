@@ -144,6 +144,47 @@ gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64
   }
 }
 
+// Sequence-parallel variant of the fold: partials -> fp64 (sum, sumsq) per (instance, group), to be
+// all-reduced across ranks by the caller, then turned into the per-channel affine with the GLOBAL count.
+__global__ void __launch_bounds__(128)
+gn_sums_kernel(const float* __restrict__ ws, int splits, int G, double* __restrict__ sums /* [n_inst, G, 2] */) {
+  __shared__ double red[2][4];
+  const int inst = blockIdx.x / G, g = blockIdx.x % G;
+  const float* base = ws + ((int64_t)inst * splits * G + g) * 2;
+  double s = 0.0, q = 0.0;
+  for (int sp = threadIdx.x; sp < splits; sp += 128) {
+    const float2 v = *reinterpret_cast<const float2*>(base + (int64_t)sp * G * 2);
+    s += (double)v.x; q += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = s; red[1][w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sums[(int64_t)blockIdx.x * 2] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+    sums[(int64_t)blockIdx.x * 2 + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  }
+}
+
+__global__ void gn_affine_kernel(const double* __restrict__ sums, int C, int G, double count, float eps,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float* __restrict__ scale_shift, int total /* n_inst * C */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int inst = i / C, c = i - inst * C, g = c / (C / G);
+  const double mean = sums[((int64_t)inst * G + g) * 2] / count;
+  double var = sums[((int64_t)inst * G + g) * 2 + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float a = rstd * gamma[c];
+  scale_shift[(int64_t)inst * 2 * C + c] = a;
+  scale_shift[(int64_t)inst * 2 * C + C + c] = beta[c] - (float)mean * a;
+}
+
 template <typename TX_, typename TY_>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int64_t R, int C,
@@ -224,6 +265,41 @@ int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_in
   gn_finalize_kernel<<<(unsigned)(n_inst * groups), 128, 0, st>>>(
       reinterpret_cast<const float*>(ws), splits, (int)C, groups, rows_per_inst, eps, gamma, beta, scale_shift);
   PB_LAUNCH_CHECK("gn_finalize_kernel");
+  return PB_OK;
+}
+
+int pb_groupnorm_sums(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_inst, int64_t rows_per_inst,
+                      int64_t C, int32_t groups, double* sums, void* ws, size_t ws_bytes, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(x && sums && ws, "pb_groupnorm_sums: null pointer");
+  PB_REQUIRE(n_inst > 0 && n_inst <= 65535 && rows_per_inst > 0 && C > 0 && groups > 0 && groups <= 32,
+             "pb_groupnorm_sums: bad sizes");
+  PB_REQUIRE(C % 4 == 0 && C % groups == 0 && ldx % 4 == 0 && C <= GN_MAX_C, "pb_groupnorm_sums: bad channel count");
+  const int splits = gn_splits(n_inst, rows_per_inst);
+  PB_REQUIRE(ws_bytes >= pb_groupnorm_ws_bytes(n_inst, rows_per_inst, C), "pb_groupnorm_sums: workspace too small");
+  cudaStream_t st = to_stream(stream);
+  int TX, TY;
+  gn_shape((int)(C / 4), &TX, &TY);
+  dim3 grid(splits, (unsigned)n_inst);
+  PB_DISPATCH_DTYPE(x_dtype, T, {
+    gn_partial_kernel<T><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const T*>(x), ldx, rows_per_inst, (int)C,
+                                                      groups, splits, TX, TY, reinterpret_cast<float*>(ws));
+  })
+  PB_LAUNCH_CHECK("gn_partial_kernel");
+  gn_sums_kernel<<<(unsigned)(n_inst * groups), 128, 0, st>>>(reinterpret_cast<const float*>(ws), splits, groups, sums);
+  PB_LAUNCH_CHECK("gn_sums_kernel");
+  return PB_OK;
+}
+
+int pb_groupnorm_affine(const double* sums, int64_t n_inst, int64_t C, int32_t groups, double count, float eps,
+                        const float* gamma, const float* beta, float* scale_shift, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(sums && gamma && beta && scale_shift && n_inst > 0 && C > 0 && groups > 0 && count > 0,
+             "pb_groupnorm_affine: bad arguments");
+  const int total = (int)(n_inst * C);
+  gn_affine_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, to_stream(stream)>>>(sums, (int)C, groups, count, eps,
+                                                                                 gamma, beta, scale_shift, total);
+  PB_LAUNCH_CHECK("gn_affine_kernel");
   return PB_OK;
 }
 

@@ -60,6 +60,8 @@ SYMBOLS = {
     "pb_groupnorm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "pb_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pb_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _i32, _vp]),
+    "pb_groupnorm_sums": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "pb_groupnorm_affine": (C.c_int, [_vp, _i64, _i64, _i32, C.c_double, _f, _vp, _vp, _vp, _vp]),
     "pb_layernorm": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _f, _vp]),
     "pb_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pb_tc_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
@@ -242,6 +244,28 @@ def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32):
     _tock(tok)
     launches += 3
     return stats
+
+
+def groupnorm_sp(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, all_reduce, global_rows, groups=32):
+    """GroupNorm whose statistics span ranks: local fp64 sums -> all_reduce(sums) -> affine -> apply."""
+    global launches
+    lib = load()
+    Cc = x.shape[1]
+    ws_bytes = lib.pb_groupnorm_ws_bytes(n_inst, rows_per_inst, Cc)
+    ws = torch.empty(ws_bytes // 4 + n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
+    stats = ws[ws_bytes // 4:]
+    sums = torch.empty(n_inst * groups * 2, dtype=torch.float64, device=x.device)
+    xp, ldx = _rows(x)
+    yp, ldy = _rows(y)
+    st = _stream()
+    _check(lib.pb_groupnorm_sums(xp, dt(x), ldx, n_inst, rows_per_inst, Cc, groups, sums.data_ptr(), ws.data_ptr(),
+                                 ws_bytes, st), "pb_groupnorm_sums")
+    all_reduce(sums)
+    _check(lib.pb_groupnorm_affine(sums.data_ptr(), n_inst, Cc, groups, float(global_rows * (Cc // groups)), eps,
+                                   gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), st), "pb_groupnorm_affine")
+    _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc,
+                                  stats.data_ptr(), int(silu), st), "pb_groupnorm_apply")
+    launches += 4
 
 
 def layernorm(x, y, gamma, beta, eps=1e-5):

@@ -113,8 +113,13 @@ class GraphedCFGStep:
         self.launches_per_step = 0
 
     def _body(self):
-        v_c = self.unet(self.x, self.ts, context=self.ctx_c, fs=self.fs, x_concat=[self.z_c])
-        v_u = self.unet(self.x, self.ts, context=self.ctx_u, fs=self.fs, x_concat=[self.z_u]) if self.cfg else None
+        cfgp = self.sampler.cfg_parallel if self.cfg else None
+        if cfgp is not None:                   # one branch per rank, then all-gather v
+            ctx, z = cfgp.my_branch((self.ctx_c, self.z_c), (self.ctx_u, self.z_u))
+            v_c, v_u = cfgp.exchange(self.unet(self.x, self.ts, context=ctx, fs=self.fs, x_concat=[z]))
+        else:
+            v_c = self.unet(self.x, self.ts, context=self.ctx_c, fs=self.fs, x_concat=[self.z_c])
+            v_u = self.unet(self.x, self.ts, context=self.ctx_u, fs=self.fs, x_concat=[self.z_u]) if self.cfg else None
         abi.ddim_cfg_step(self.x, v_c, v_u, self.noise, self.x, self.pred_x0, self.cfg_scale, self.rescale,
                           self.temperature, self.table, self.step_index, True, self.ws)
 
@@ -148,6 +153,7 @@ class GraphedCFGStep:
         self.ts.fill_(int(ddpm_step))
         # same call (shape, device) as the reference's noise_like -> identical generator consumption
         self.noise.copy_(torch.randn(self.noise.shape, device=self.noise.device) if noise is None else noise)
+        self.sampler._sync_noise(self.noise)
         self.graph.replay()
         abi.launches += self.launches_per_step
         return self.x, self.pred_x0
@@ -163,6 +169,12 @@ class DDIMSampler(object):
         self._tables = {}
         #: capture the CFG step as a CUDA graph when the native U-Net is underneath (set False to run eagerly)
         self.use_cuda_graph = True
+        #: `pandora_b200.dist.CFGParallel`: evaluate the cond / uncond branches on two ranks (one all-gather of v
+        #: per step); None = both branches on this rank
+        self.cfg_parallel = None
+        #: process group of all ranks denoising the SAME clip (CFG x sequence parallel): per-step noise is
+        #: broadcast from its first rank so every rank applies the identical update
+        self.replica_group = None
 
     def register_buffer(self, name, attr):
         if isinstance(attr, torch.Tensor) and attr.device != self.model.device:
@@ -358,6 +370,12 @@ class DDIMSampler(object):
         g.capture()
         return g
 
+    def _sync_noise(self, noise):
+        if self.replica_group is not None:
+            import torch.distributed as dist
+            dist.broadcast(noise, src=dist.get_global_rank(self.replica_group, 0), group=self.replica_group)
+        return noise
+
     # --------------------------------------------------------------------------------- one step
     def _denoise(self, x, t, c, **kwargs):
         """model.apply_model, short-circuited to the native U-Net when the wrapper is 'hybrid'."""
@@ -385,12 +403,16 @@ class DDIMSampler(object):
         device, in_dtype = x.device, x.dtype
         x32 = x.float().contiguous()
         cfg = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.)
-        v_c = self._denoise(x32, t, c, **kwargs).float().contiguous()
+        if cfg and not isinstance(c, (torch.Tensor, dict)):
+            raise NotImplementedError
         v_u = None
-        if cfg:
-            if not isinstance(c, (torch.Tensor, dict)):
-                raise NotImplementedError
-            v_u = self._denoise(x32, t, unconditional_conditioning, **kwargs).float().contiguous()
+        if cfg and self.cfg_parallel is not None:
+            mine = self.cfg_parallel.my_branch(c, unconditional_conditioning)
+            v_c, v_u = self.cfg_parallel.exchange(self._denoise(x32, t, mine, **kwargs).float().contiguous())
+        else:
+            v_c = self._denoise(x32, t, c, **kwargs).float().contiguous()
+            if cfg:
+                v_u = self._denoise(x32, t, unconditional_conditioning, **kwargs).float().contiguous()
         shape = x.shape
         if repeat_noise:
             noise = torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
@@ -399,6 +421,7 @@ class DDIMSampler(object):
         if noise_dropout > 0.:
             # dropout acts on sigma*noise*temperature in the reference; sigma, temperature are scalars
             noise = torch.nn.functional.dropout(noise, p=noise_dropout)
+        noise = self._sync_noise(noise.contiguous())
         table, idx = self._step_table(use_original_steps)
         x_prev, pred_x0 = torch.empty_like(x32), torch.empty_like(x32)
         ws = torch.empty(4 * shape[0], dtype=torch.float64, device=device) if (cfg and guidance_rescale > 0) else None

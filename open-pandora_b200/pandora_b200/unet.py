@@ -182,6 +182,9 @@ class UNetModel(nn.Module):
         self.compute_mode = None
         #: "auto" uses the tcgen05 kernels whenever they accept the shape (bf16 mode), "simt" never.
         self.kernel_impl = "auto"
+        #: a `pandora_b200.dist.SequenceParallel` to run ONE clip across its ranks (frames sharded for the
+        #: per-frame layers, pixels for the temporal layers); None = single GPU.  Batch must be 1.
+        self.sequence_parallel = None
 
         mc, ted, nhc = model_channels, model_channels * 4, num_head_channels
         att = set(attention_resolutions)
@@ -253,13 +256,16 @@ class UNetModel(nn.Module):
         for key, entry in list(self._ctx_cache.items()):
             if entry.get("__keepalive__") is context:
                 r = _Runner.__new__(_Runner)
-                r.m, r.context, r.dev, r.T = self, context, context.device, frames
+                r.m, r.context, r.dev = self, context, context.device
+                r.sp, r.Tf = self.sequence_parallel, frames
+                r.T = frames if r.sp is None else frames // r.sp.P
                 r.mode = key[4]
                 r.opdt = torch.bfloat16 if r.mode == "bf16" else torch.float32
                 r.use_tc = r.mode == "bf16" and self.kernel_impl == "auto" and abi.supports_tc()
                 r.pack, r.sd = self._packs.setdefault(r.mode, {}), None
                 r._context_kv(reuse=entry)
-                new_key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype, r.mode, frames)
+                new_key = (context.data_ptr(), context._version, tuple(context.shape), context.dtype, r.mode, r.T,
+                           None if r.sp is None else r.sp.rank)
                 del self._ctx_cache[key]
                 self._ctx_cache[new_key] = entry
 
@@ -316,6 +322,14 @@ class _Runner:
         self.pack = model._packs.setdefault(mode, {})
         self.sd = None
         self.b, _, self.T, self.H0, self.W0 = x.shape
+        self.sp = model.sequence_parallel
+        self.Tf = self.T                       # frames of the clip; self.T = frames held by this rank
+        if self.sp is not None:
+            if self.b != 1:
+                raise RuntimeError("sequence parallelism shards a single clip (batch 1)")
+            down = 2 ** (len(model.channel_mult) - 1)
+            self.sp.check(self.Tf, (self.H0 // down) * (self.W0 // down))
+            self.T = self.Tf // self.sp.P
 
     # ---- buffers
     def new(self, rows, cols, dtype):
@@ -394,10 +408,16 @@ class _Runner:
         abi.copy_rows(a, y)
         return y
 
-    def gn(self, x, prefix, n_inst, eps, silu, out_dtype=None):
+    def gn(self, x, prefix, n_inst, eps, silu, out_dtype=None, clip_wide=False):
+        """clip_wide: statistics span all frames and pixels of a sample (temporal blocks); under sequence
+        parallelism every rank holds a slice, so the (sum, sumsq) pairs are all-reduced."""
         y = self.new(x.shape[0], x.shape[1], out_dtype or self.opdt)
-        abi.groupnorm(x, y, n_inst, x.shape[0] // n_inst, self.vec(prefix + "weight"), self.vec(prefix + "bias"),
-                      eps, silu)
+        rows = x.shape[0] // n_inst
+        if clip_wide and self.sp is not None:
+            abi.groupnorm_sp(x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu,
+                             self.sp.all_reduce_sum, rows * self.sp.P)
+        else:
+            abi.groupnorm(x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu)
         return y
 
     def ln(self, x, prefix):
@@ -426,7 +446,7 @@ class _Runner:
     def convt3(self, a, wname, bname, frame_rows, out_dtype, residual=None):
         w = self.conv_w(wname)
         return self.gemm(a, w, w.shape[0], out_dtype, bias=self.vec(bname), residual=residual,
-                         mode=abi.A_CONVT3, convt=(a.shape[1], self.T, frame_rows))
+                         mode=abi.A_CONVT3, convt=(a.shape[1], self.Tf, frame_rows))
 
     # ---- blocks -------------------------------------------------------------------------------
     def res_block(self, blk, x, H, W):
@@ -444,12 +464,16 @@ class _Runner:
         h = self.conv3x3(a, p + "out_layers.3.weight", p + "out_layers.3.bias", H, W, torch.float32, residual=skip)
         if blk.use_temporal_conv:
             q = p + "temopral_conv."
+            hw = H * W
+            if self.sp is not None:                 # frames -> pixels: every rank gets all T frames of hw/P pixels
+                h = self.sp.frames_to_pixels(h, self.T, hw)
+                hw //= self.sp.P
             y = h
             for i, ci in ((1, 2), (2, 3), (3, 3), (4, 3)):
-                a = self.gn(y, f"{q}conv{i}.0.", self.b, 1e-5, True)
-                y = self.convt3(a, f"{q}conv{i}.{ci}.weight", f"{q}conv{i}.{ci}.bias", H * W, torch.float32,
+                a = self.gn(y, f"{q}conv{i}.0.", self.b, 1e-5, True, clip_wide=True)
+                y = self.convt3(a, f"{q}conv{i}.{ci}.weight", f"{q}conv{i}.{ci}.bias", hw, torch.float32,
                                 residual=h if i == 4 else None)
-            h = y
+            h = y if self.sp is None else self.sp.pixels_to_frames(y, self.T, H * W)
         return h
 
     def _attn(self, q, k, v, out, batch, heads, n_q, n_kv, accumulate=False):
@@ -525,14 +549,18 @@ class _Runner:
     def temporal_transformer(self, mod, x, H, W):
         """Rows stay in (b, t, p) order; attention gathers the T frames of a pixel by stride."""
         p = mod._pfx
-        HW, T = H * W, self.T
-        a = self.gn(x, p + "norm.", self.b, 1e-6, False)
+        HW, T = H * W, self.Tf
+        if self.sp is not None:
+            x = self.sp.frames_to_pixels(x, self.T, HW)
+            HW //= self.sp.P
+        a = self.gn(x, p + "norm.", self.b, 1e-6, False, clip_wide=True)
         t = self.linear(a, p + "proj_in.weight", p + "proj_in.bias", torch.float32)
         addr = dict(batch=self.b * HW, n=T,
                     op=lambda ten, off, ld: abi.operand(ten, HW, T * HW * ld, ld, HW * ld, off),
                     o=lambda ld: (HW, T * HW * ld, ld, HW * ld))
         t = self._blocks(mod, t, mod.n_heads, addr, None)
-        return self.linear(t, p + "proj_out.weight", p + "proj_out.bias", torch.float32, residual=x)
+        y = self.linear(t, p + "proj_out.weight", p + "proj_out.bias", torch.float32, residual=x)
+        return y if self.sp is None else self.sp.pixels_to_frames(y, self.T, H * W)
 
     # ---- conditioning -------------------------------------------------------------------------
     def _context_kv(self, reuse=None):
@@ -540,20 +568,26 @@ class _Runner:
         They depend only on (context, weights): cached across the 50 steps x 2 CFG branches
         (the reference recomputes them in every forward and for every frame, attention.py:89-94)."""
         ctx, m = self.context, self.m
-        key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), ctx.dtype, self.mode, self.T)
+        key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), ctx.dtype, self.mode, self.T,
+               None if self.sp is None else self.sp.rank)
         hit = m._ctx_cache.get(key) if reuse is None else None
         if hit is not None:
             m._ctx_cache.move_to_end(key)
             return hit
         b, L, D = ctx.shape
         T = self.T
-        per_frame = L == TEXT_LEN + IMG_TOKENS * T
+        per_frame = L == TEXT_LEN + IMG_TOKENS * self.Tf
         c = ctx if ctx.dtype in (torch.float32, torch.bfloat16) else ctx.float()
         n_text = min(L, TEXT_LEN)
         # one-off slicing of the conditioning tensor (once per sampler call, not per step)
         text = self.cast(c[:, :n_text].reshape(b * n_text, D), self.opdt)
         n_img_rows = max(L - TEXT_LEN, 0)
-        img = self.cast(c[:, TEXT_LEN:].reshape(b * n_img_rows, D), self.opdt) if n_img_rows else None
+        img_src = c[:, TEXT_LEN:]
+        if per_frame and self.sp is not None:       # this rank only attends with its own frames' image tokens
+            t0, t1 = self.sp.frame_range(self.Tf)
+            img_src = img_src[:, t0 * IMG_TOKENS:t1 * IMG_TOKENS]
+            n_img_rows = img_src.shape[1]
+        img = self.cast(img_src.reshape(b * n_img_rows, D), self.opdt) if n_img_rows else None
         out = {}
         for mod in m.modules():
             if not isinstance(mod, SpatialTransformer):
@@ -661,6 +695,11 @@ class _Runner:
         xin = xin.contiguous()
         if x2 is not None:
             x2 = x2.to(xin.dtype).contiguous()
+        if self.sp is not None:
+            t0, t1 = self.sp.frame_range(T)
+            xin = xin[:, :, t0:t1].contiguous()
+            x2 = None if x2 is None else x2[:, :, t0:t1].contiguous()
+            T = t1 - t0
         self._embeddings()
         self.ctx_kv = self._context_kv()
         if cin % 4:
@@ -685,4 +724,6 @@ class _Runner:
         y = self.conv3x3(a, "out.2.weight", "out.2.bias", H, W, torch.float32, wdtype=torch.float32)
         out = torch.empty((b, m.out_channels, T, H, W), dtype=xin.dtype, device=self.dev)
         abi.rows_to_video(y, out, b, m.out_channels, T, H * W)
+        if self.sp is not None:
+            out = self.sp.gather_frames(out)
         return out if out.dtype == x.dtype else out.to(x.dtype)

@@ -1,0 +1,98 @@
+"""Multi-GPU (>= 2 devices, NCCL): a clip denoised sequence-parallel / CFG-parallel equals the single-GPU result.
+Skipped on single-GPU boxes; run with `gpurun --gpus 2 -- python -m pytest tests/test_sp_gpu.py -m gpu`."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(dtype):
+    from pandora_b200 import UNetModel, config
+    from pandora_b200.synthetic import randomize_module_, synth_inputs
+    p = config.small_unet()
+    m = randomize_module_(UNetModel(**p).eval(), 21).to(device="cuda", dtype=dtype)
+    inp = {k: v.cuda() for k, v in synth_inputs(1, (4, 16, 16, 16), p["context_dim"], seed=5).items()}
+    return p, m, inp
+
+
+def _worker(rank, world, port, mode, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from pandora_b200 import DDIMSampler, LatentDiffusionLite, config
+        from pandora_b200.dist import CFGParallel, SequenceParallel
+        dtype = torch.bfloat16 if mode.endswith("bf16") else torch.float32
+        p, m, inp = _build(dtype)
+        t = torch.tensor([499], device="cuda")
+        if mode.startswith("unet"):
+            m.sequence_parallel = SequenceParallel()
+            y = m(inp["x"], t, context=inp["context"], x_concat=[inp["c_concat"]])
+            ret[rank] = y.float().cpu()
+        else:
+            model = LatentDiffusionLite(m, **config.DIFFUSION_512).cuda()
+            s = DDIMSampler(model)
+            if mode.startswith("cfg"):
+                s.cfg_parallel = CFGParallel()
+            else:
+                m.sequence_parallel = SequenceParallel()
+            s.replica_group = dist.group.WORLD
+            s.use_cuda_graph = mode.split("-")[1] == "graph"
+            cond = dict(c_crossattn=[inp["context"]], c_concat=[inp["c_concat"]])
+            uc = dict(c_crossattn=[inp["uc_context"]], c_concat=[inp["c_concat"]])
+            torch.manual_seed(100 + rank)         # different seeds: the broadcast must make the noise identical
+            x, _ = s.sample(S=4, batch_size=1, shape=(4, 16, 16, 16), conditioning=cond, unconditional_conditioning=uc,
+                            unconditional_guidance_scale=7.5, eta=1.0, x_T=inp["x"], verbose=False,
+                            timestep_spacing="uniform_trailing", guidance_rescale=0.7)
+            ret[rank] = x.float().cpu()
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(mode, world=2):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), mode, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+@pytest.mark.parametrize("mode,tol", [("unet-fp32", 1e-4), ("unet-bf16", 2e-2)])
+def test_sequence_parallel_unet_matches_single_gpu(mode, tol):
+    outs = _run(mode)
+    dtype = torch.bfloat16 if mode.endswith("bf16") else torch.float32
+    p, m, inp = _build(dtype)
+    ref = m(inp["x"], torch.tensor([499], device="cuda"), context=inp["context"], x_concat=[inp["c_concat"]]).float().cpu()
+    assert torch.equal(outs[0], outs[1])
+    assert rel_l2(outs[0], ref) < tol
+
+
+@pytest.mark.parametrize("mode", ["cfg-eager-fp32", "cfg-graph-fp32", "sp-eager-fp32", "sp-graph-fp32"])
+def test_parallel_sampler_matches_single_gpu(mode):
+    outs = _run(mode)
+    from pandora_b200 import DDIMSampler, LatentDiffusionLite, config
+    p, m, inp = _build(torch.float32)
+    s = DDIMSampler(LatentDiffusionLite(m, **config.DIFFUSION_512).cuda())
+    cond = dict(c_crossattn=[inp["context"]], c_concat=[inp["c_concat"]])
+    uc = dict(c_crossattn=[inp["uc_context"]], c_concat=[inp["c_concat"]])
+    torch.manual_seed(100)                        # rank 0's seed: its noise is what gets broadcast
+    ref, _ = s.sample(S=4, batch_size=1, shape=(4, 16, 16, 16), conditioning=cond, unconditional_conditioning=uc,
+                      unconditional_guidance_scale=7.5, eta=1.0, x_T=inp["x"], verbose=False,
+                      timestep_spacing="uniform_trailing", guidance_rescale=0.7)
+    assert torch.equal(outs[0], outs[1])
+    assert rel_l2(outs[0], ref.float().cpu()) < 1e-4
