@@ -73,6 +73,10 @@ typedef struct pb_gemm_args {
   int32_t cin, in_h, in_w, out_h, out_w, stride, upsample;
   /* PB_A_CONVT3: rows ordered (b, t, p): frames = T, pixels per frame = HW                       */
   int32_t frames, frame_rows;
+  /* optional scratch for pb_tc_gemm's split-K (small-M launches that would leave most SMs idle): size from
+     pb_tc_gemm_workspace_bytes(); NULL or too small => no split (results identical up to fp32 summation order) */
+  void* workspace;
+  int64_t workspace_bytes;
 } pb_gemm_args;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -96,6 +100,7 @@ int pb_gemm(const pb_gemm_args* args, pb_stream_t stream);
  * Same argument block and semantics as pb_gemm.  Returns PB_EUNSUPPORTED for shapes it cannot take
  * (the caller then decides; there is no silent fallback inside the library).                      */
 int pb_tc_gemm(const pb_gemm_args* args, pb_stream_t stream);
+size_t pb_tc_gemm_workspace_bytes(const pb_gemm_args* args);
 
 /* ---- GroupNorm(32) (+SiLU) ---------------------------------------------------------------------
  * Replaces nn.GroupNorm at basics.py:76-88, openaimodel3d.py:155,179,259-268,547 (eps 1e-5) and

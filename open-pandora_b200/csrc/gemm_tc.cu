@@ -60,6 +60,9 @@ struct TcParams {
   int W, H;              // CONV3X3: image size ; CONVT3: W = HW (pixels per frame), H = T
   int tiles_x, tiles_y;  // CONV3X3: W/bw, H/bh ; CONVT3: HW/bw, T/bh
   int cstride;           // CONV3X3 spatial stride (1 or 2); W/H above are OUTPUT sizes
+  int splits;            // split-K ways (1 = off); split s covers k-iterations [s*kps, (s+1)*kps)
+  int kps;               // k-iterations per split
+  int64_t split_stride;  // elements between the partial outputs of consecutive splits
 };
 
 template <int MODE>
@@ -119,7 +122,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================================================== TMA producer
     if (lane == 0) {
       int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_tiles * p.splits; work += gridDim.x) {
+        const int tile = work / p.splits, split = work - tile * p.splits;
+        const int it0 = split * p.kps, it1 = (it0 + p.kps < k_iters) ? it0 + p.kps : k_iters;
         const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
         int cx = 0, cy = 0, cn = 0;
         if (MODE != PB_A_LINEAR) {
@@ -127,7 +132,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           cy = ((m_tile / p.tiles_x) % p.tiles_y) * p.bh;
           cn = (m_tile / (p.tiles_x * p.tiles_y)) * p.bn_img;
         }
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = it0; it < it1; ++it) {
           const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
@@ -158,11 +163,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < total_tiles * p.splits; work += gridDim.x) {
+        const int split = work % p.splits;
+        const int it0 = split * p.kps, it1 = (it0 + p.kps < k_iters) ? it0 + p.kps : k_iters;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
-        for (int it = 0; it < k_iters; ++it) {
+        for (int it = it0; it < it1; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_base + stage * stage_bytes;
@@ -171,7 +178,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((it - it0) | k) != 0);
           }
           umma_commit(empty_bar(stage));
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -187,10 +194,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = threadIdx.x - 64;         // 0..127
     const int b_row0 = et >> 3;              // phase B: rows b_row0 + 16*i, 4 columns at b_col
     const int b_col = (et & 7) * 4;
-    TC* C = reinterpret_cast<TC*>(p.c);
     int acc = 0, acc_phase = 0;
     uint32_t chunk_counter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_tiles * p.splits; work += gridDim.x) {
+      const int tile = work / p.splits, split = work - tile * p.splits;
+      TC* C = reinterpret_cast<TC*>(p.c) + (int64_t)split * p.split_stride;   // split-K: partials, reduced afterwards
       const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
       // rows this thread stores in phase B (fixed for the tile)
       int64_t rows_m[8];
@@ -299,6 +307,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// split-K fold: C = sum_s partial[s] (+bias +rowbias +residual), deterministic order
+template <typename TC>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int N, TC* __restrict__ c, int64_t ldc,
+                     const float* __restrict__ bias, const float* __restrict__ rowbias, int64_t ldrb, int64_t rb_rows,
+                     const float* __restrict__ residual, int64_t ldr) {
+  const int64_t nv = N >> 2, total = M * nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / nv;
+    const int n = (int)(i - m * nv) * 4;
+    float4 a = *reinterpret_cast<const float4*>(ws + m * N + n);
+    for (int s = 1; s < splits; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(ws + ((int64_t)s * M + m) * N + n);
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    if (bias) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n)); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    if (rowbias) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(rowbias + (m / rb_rows) * ldrb + n));
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    if (residual) { const float4 t = *reinterpret_cast<const float4*>(residual + m * ldr + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+    const float o[4] = {a.x, a.y, a.z, a.w};
+    store4(c + m * ldc + n, o);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -355,11 +389,30 @@ static bool pick_brick(int W, int H, int N, int* bw, int* bh, int* bn) {
   return false;
 }
 
-static int pick_block_n(int n_cols, int cap) {
-  // largest multiple of 16 that divides n_cols, <= cap
-  for (int bn = cap - cap % 16; bn >= 16; bn -= 16)
-    if (n_cols % bn == 0) return bn;
-  return 0;
+static int num_sms();
+
+// Tile width: a multiple of 16 dividing n_cols, <= cap, minimising (waves over the SMs) x (per-tile cost);
+// the +64 charges the A-tile traffic every tile pays regardless of its width, so narrow tiles only win when
+// they remove a whole wave.
+static int pick_block_n(int n_cols, int cap, int m_tiles) {
+  int best = 0;
+  long best_cost = 0;
+  for (int bn = cap - cap % 16; bn >= 64 || (best == 0 && bn >= 16); bn -= 16) {
+    if (n_cols % bn != 0) continue;
+    const long tiles = (long)m_tiles * (n_cols / bn);
+    const long waves = (tiles + num_sms() - 1) / num_sms();
+    const long cost = waves * (bn + 64);
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+// split-K ways for launches that would leave most SMs idle (H/8 level: 5 m-tiles)
+static int pick_splits(int tiles, int k_iters) {
+  if (tiles * 2 > num_sms() || k_iters < 8) return 1;
+  int s = num_sms() / tiles;
+  if (s > k_iters / 4) s = k_iters / 4;
+  return s < 1 ? 1 : s;
 }
 
 static int num_sms() {
@@ -382,7 +435,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_kernel)");
     configured = true;
   }
-  int grid = p.m_tiles * p.n_tiles;
+  int grid = p.m_tiles * p.n_tiles * p.splits;
   if (grid > num_sms()) grid = num_sms();
   kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
   PB_LAUNCH_CHECK("tc_gemm_kernel");
@@ -425,12 +478,6 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   p.rb_rows = a->rowbias_rows > 0 ? a->rowbias_rows : 1;
   p.N = (int)a->N; p.epi = a->epilogue;
   p.geglu_half = geglu ? (int)(a->N / 2) : 0;
-
-  const int n_cols = geglu ? (int)(a->N / 2) : (int)a->N;   // output columns
-  int bn_out = pick_block_n(n_cols, geglu ? 128 : 256);
-  if (bn_out == 0) TC_UNSUPPORTED("pb_tc_gemm: no tile width divides N=%d", n_cols);
-  p.block_n = geglu ? 2 * bn_out : bn_out;
-  p.n_tiles = n_cols / bn_out;
 
   CUtensorMap tmA, tmB;
   const int cin = a->a_mode == PB_A_LINEAR ? (int)a->K : a->cin;
@@ -477,6 +524,23 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box, nullptr);
   }
   if (rc != PB_OK) return rc;
+  const int n_cols = geglu ? (int)(a->N / 2) : (int)a->N;   // output columns
+  const int bn_out = pick_block_n(n_cols, geglu ? 128 : 256, p.m_tiles);
+  if (bn_out == 0) TC_UNSUPPORTED("pb_tc_gemm: no tile width divides N=%d", n_cols);
+  p.block_n = geglu ? 2 * bn_out : bn_out;
+  p.n_tiles = n_cols / bn_out;
+  // split-K (deterministic: fp32 partials in the caller's workspace + a fold kernel) when the grid is tiny
+  const int k_iters = p.taps * p.k_chunks;
+  p.splits = 1; p.kps = k_iters; p.split_stride = 0;
+  const int want_splits = geglu ? 1 : pick_splits(p.m_tiles * p.n_tiles, k_iters);
+  if (want_splits > 1 && a->workspace &&
+      a->workspace_bytes >= (int64_t)want_splits * a->M * a->N * (int64_t)sizeof(float)) {
+    p.kps = (k_iters + want_splits - 1) / want_splits;
+    p.splits = (k_iters + p.kps - 1) / p.kps;
+    p.split_stride = a->M * a->N;
+    p.c = a->workspace; p.ldc = a->N; p.epi = 0;
+    p.bias = nullptr; p.rowbias = nullptr; p.residual = nullptr;
+  }
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t str[1] = {(uint64_t)a->K * esz};
@@ -490,10 +554,45 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 2 * EPI_STAGE_BYTES + BAR_BYTES;
 
   cudaStream_t st = to_stream(stream);
-  const int cd = a->c_dtype;
+  const int cd = p.splits > 1 ? PB_F32 : a->c_dtype;
   if (a->a_mode == PB_A_LINEAR)
-    return geglu ? launch_c<PB_A_LINEAR, true>(tmA, tmB, p, smem, st, cd) : launch_c<PB_A_LINEAR, false>(tmA, tmB, p, smem, st, cd);
-  if (a->a_mode == PB_A_CONV3X3) return launch_c<PB_A_CONV3X3, false>(tmA, tmB, p, smem, st, cd);
-  return launch_c<PB_A_CONVT3, false>(tmA, tmB, p, smem, st, cd);
+    rc = geglu ? launch_c<PB_A_LINEAR, true>(tmA, tmB, p, smem, st, cd) : launch_c<PB_A_LINEAR, false>(tmA, tmB, p, smem, st, cd);
+  else if (a->a_mode == PB_A_CONV3X3) rc = launch_c<PB_A_CONV3X3, false>(tmA, tmB, p, smem, st, cd);
+  else rc = launch_c<PB_A_CONVT3, false>(tmA, tmB, p, smem, st, cd);
+  if (rc != PB_OK || p.splits == 1) return rc;
+  const int64_t total = a->M * (a->N / 4);
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  const float* ws = reinterpret_cast<const float*>(a->workspace);
+  const float* bias = (a->epilogue & PB_EPI_BIAS) ? a->bias : nullptr;
+  const float* rowb = (a->epilogue & PB_EPI_ROWBIAS) ? a->rowbias : nullptr;
+  const float* resid = (a->epilogue & PB_EPI_RESIDUAL) ? a->residual : nullptr;
+  const int64_t rbr = a->rowbias_rows > 0 ? a->rowbias_rows : 1;
+  if (a->c_dtype == PB_F32)
+    splitk_reduce_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(ws, p.splits, a->M, (int)a->N, reinterpret_cast<float*>(a->c),
+                                                                  a->ldc, bias, rowb, a->ld_rowbias, rbr, resid, a->ldr);
+  else
+    splitk_reduce_kernel<bf16><<<(unsigned)blocks, 256, 0, st>>>(ws, p.splits, a->M, (int)a->N, reinterpret_cast<bf16*>(a->c),
+                                                                 a->ldc, bias, rowb, a->ld_rowbias, rbr, resid, a->ldr);
+  PB_LAUNCH_CHECK("splitk_reduce_kernel");
+  return PB_OK;
 #undef TC_UNSUPPORTED
+}
+
+extern "C" size_t pb_tc_gemm_workspace_bytes(const pb_gemm_args* a) {
+  // upper bound for the split-K partials of this problem (0 when split-K will not be used)
+  using namespace pb::tc;
+  if (!a || a->M <= 0 || a->N <= 0 || (a->epilogue & PB_EPI_GEGLU)) return 0;
+  const int m_tiles = (int)((a->M + BLOCK_M - 1) / BLOCK_M);
+  if (m_tiles * 2 > num_sms()) return 0;
+  const int cin = a->a_mode == PB_A_LINEAR ? (int)a->K : a->cin;
+  const int taps = a->a_mode == PB_A_LINEAR ? 1 : (a->a_mode == PB_A_CONV3X3 ? 9 : 3);
+  const int k_iters = taps * (cin / BLOCK_K);
+  int worst = 1;
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    if (a->N % bn) continue;
+    const int s = pick_splits(m_tiles * (int)(a->N / bn), k_iters);
+    if (s > worst) worst = s;
+  }
+  return worst > 1 ? (size_t)worst * a->M * a->N * sizeof(float) : 0;
 }

@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("cin", C.c_int32), ("in_h", C.c_int32), ("in_w", C.c_int32), ("out_h", C.c_int32),
         ("out_w", C.c_int32), ("stride", C.c_int32), ("upsample", C.c_int32),
         ("frames", C.c_int32), ("frame_rows", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -57,6 +58,7 @@ SYMBOLS = {
     "pb_device_supports_tc": (C.c_int, []),
     "pb_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "pb_tc_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "pb_tc_gemm_workspace_bytes": (_sz, [C.POINTER(GemmArgs)]),
     "pb_groupnorm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "pb_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pb_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _i32, _vp]),
@@ -213,6 +215,12 @@ def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=
         g.cin, g.frames, g.frame_rows = convt
     lib = load()
     fn = lib.pb_tc_gemm if tc else lib.pb_gemm
+    ws = None
+    if tc and g.M <= 9472:                     # split-K scratch only matters for launches with < 74 row tiles
+        nb = lib.pb_tc_gemm_workspace_bytes(C.byref(g))
+        if nb:
+            ws = torch.empty(nb, dtype=torch.uint8, device=a.device)
+            g.workspace, g.workspace_bytes = ws.data_ptr(), nb
     tok = _tick(("tc_" if tc else "simt_") + ("gemm", "conv3x3", "convt3")[mode] + ("_geglu" if geglu else ""),
                 2 * g.M * g.N * g.K, (g.M * g.K // (1, 9, 3)[mode] + g.N * g.K) * a.element_size() + _nbytes(c, residual))
     rc = fn(C.byref(g), _stream())

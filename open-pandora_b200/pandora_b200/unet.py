@@ -720,8 +720,19 @@ class _Runner:
             abi.copy_rows(h, cat[:, :h.shape[1]])
             abi.copy_rows(s, cat[:, h.shape[1]:])
             h, H, W = self.run_block(seq, cat, H, W)
-        a = self.gn(h, "out.0.", b * T, 1e-5, True, out_dtype=torch.float32)
-        y = self.conv3x3(a, "out.2.weight", "out.2.bias", H, W, torch.float32, wdtype=torch.float32)
+        if self.use_tc:
+            # 320 -> 4 head conv on the tensor cores: output channels zero-padded to one 16-wide UMMA tile
+            oc = m.out_channels
+            w16 = self.w(("convpad16", "out.2.weight"), lambda: torch.cat(
+                [self.conv_w("out.2.weight"), torch.zeros(16 - oc, 9 * h.shape[1], dtype=self.opdt, device=self.dev)], 0))
+            b16 = self.w(("vecpad16", "out.2.bias"), lambda: torch.cat(
+                [self.vec("out.2.bias"), torch.zeros(16 - oc, dtype=torch.float32, device=self.dev)], 0))
+            a = self.gn(h, "out.0.", b * T, 1e-5, True)
+            y = self.gemm(a, w16, 16, torch.float32, bias=b16, mode=abi.A_CONV3X3,
+                          conv=(h.shape[1], H, W, H, W, 1, 0), M=b * T * H * W)[:, :oc]
+        else:
+            a = self.gn(h, "out.0.", b * T, 1e-5, True, out_dtype=torch.float32)
+            y = self.conv3x3(a, "out.2.weight", "out.2.bias", H, W, torch.float32, wdtype=torch.float32)
         out = torch.empty((b, m.out_channels, T, H, W), dtype=xin.dtype, device=self.dev)
         abi.rows_to_video(y, out, b, m.out_channels, T, H * W)
         if self.sp is not None:

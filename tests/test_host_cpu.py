@@ -28,7 +28,7 @@ def test_header_and_binding_agree_and_library_exports_everything():
 def test_struct_layouts_match_header_field_order():
     assert [f[0] for f in abi.GemmArgs._fields_][:9] == ["a", "w", "c", "bias", "rowbias", "residual", "M", "N", "K"]
     assert abi.GemmArgs.M.offset == 48 and abi.GemmArgs.a_dtype.offset == 112
-    assert abi.AttnOperand.rs.offset == 32 and abi.AttnArgs.out.offset == 120
+    assert abi.AttnOperand.rs.offset == 32 and abi.AttnArgs.out.offset == 120 and abi.GemmArgs.workspace.offset == 168
 
 
 @pytest.mark.parametrize("cfg", [config.small_unet(), config.UNET_512])
