@@ -20,6 +20,7 @@
 //   CONVT3   4-D map [b][t][p][c]; tap kt = box shifted by kt-1 frames (zero-filled outside the clip)
 // A 128-row tile is a BW x BH x BN (x, y, image) or BP x BT (pixel, frame) brick chosen so the brick tiles
 // the tensor exactly.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -63,6 +64,7 @@ struct TcParams {
   int splits;            // split-K ways (1 = off); split s covers k-iterations [s*kps, (s+1)*kps)
   int kps;               // k-iterations per split
   int64_t split_stride;  // elements between the partial outputs of consecutive splits
+  int pair;              // 1 = CTA-pair kernel (cta_group::2): block_n is the width of the 256-row pair tile
 };
 
 template <int MODE>
@@ -307,6 +309,281 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ================================================================================================
+// CTA-pair variant (cta_group::2): two SMs of a TPC compute one 256 x block_n tile.  Each CTA stages ITS
+// 128 rows of A and ITS half (block_n/2 rows) of W, the leader CTA issues one UMMA M=256 that reads both
+// shared memories, and each CTA's tensor memory receives its own 128 accumulator rows.  Per SM this moves
+// 16 KiB + block_n*64 B per k-step instead of 16 KiB + block_n*128 B, so the same shared-memory ring covers
+// 1.5x more FLOPs of latency and L2 traffic per FLOP drops by a third.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  const uint32_t z0 = 0, z1 = 0, z2 = 0, z3 = 0, z4 = 0, z5 = 0, z6 = 0, z7 = 0;   // disable-output-lane masks
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z0), "r"(z1), "r"(z2), "r"(z3),
+      "r"(z4), "r"(z5), "r"(z6), "r"(z7)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on the same barrier of BOTH CTAs
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int MODE, bool GEGLU, typename TC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int half_n = p.block_n >> 1;                        // W rows staged by this CTA
+  const int stage_bytes = A_STAGE_BYTES + half_n * BLOCK_K * 2;
+  const uint32_t epi_base = smem_base + p.stages * stage_bytes;
+  const uint32_t bar_base = epi_base + 2 * EPI_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // used in the leader only
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };       // one per CTA (multicast commit)
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };   // one per CTA (multicast commit)
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };  // leader only, 8 arrivals
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int pair_m_tiles = (p.m_tiles + 1) >> 1;
+  const int total_work = pair_m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_slot, TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int work = pair_id; work < total_work; work += num_pairs) {
+        const int n_tile = work % p.n_tiles;
+        const int m_tile = 2 * (work / p.n_tiles) + (int)rank;
+        int cx = 0, cy = 0, cn = 0;
+        if (MODE != PB_A_LINEAR) {
+          cx = (m_tile % p.tiles_x) * p.bw;
+          cy = ((m_tile / p.tiles_x) % p.tiles_y) * p.bh;
+          cn = (m_tile / (p.tiles_x * p.tiles_y)) * p.bn_img;
+        }
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t a_dst = smem_base + stage * stage_bytes;
+          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+          if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)stage_bytes);   // bytes of BOTH CTAs
+          if (MODE == PB_A_LINEAR) {
+            tma_load_2d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
+          } else if (MODE == PB_A_CONV3X3) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx * p.cstride + kx - 1,
+                             cy * p.cstride + ky - 1, cn);
+          } else {
+            tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
+          }
+          const int kcol = it * BLOCK_K;
+          // GEGLU: CTA 0 stages the value rows, CTA 1 the gate rows of the same output columns
+          const int wrow = GEGLU ? (int)rank * p.geglu_half + n_tile * half_n : n_tile * p.block_n + (int)rank * half_n;
+          tma_load_2d_pair(b_dst, &tmB, full_bar(stage), kcol, wrow);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, (uint32_t)p.block_n);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int work = pair_id; work < total_work; work += num_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * stage_bytes;
+          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+          const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+          umma_commit_pair(empty_bar(stage));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================== epilogue (warps 2..5, both CTAs)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const int b_row0 = et >> 3;
+    const int b_col = (et & 7) * 4;
+    TC* C = reinterpret_cast<TC*>(p.c);
+    int acc = 0, acc_phase = 0;
+    uint32_t chunk_counter = 0;
+    for (int work = pair_id; work < total_work; work += num_pairs) {
+      const int n_tile = work % p.n_tiles;
+      const int m_tile = 2 * (work / p.n_tiles) + (int)rank;
+      int64_t rows_m[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t m = m_tile < p.m_tiles ? out_row<MODE>(p, m_tile, b_row0 + 16 * i) : p.M;
+        rows_m[i] = m < p.M ? m : -1;
+      }
+      const int out_cols = GEGLU ? (p.block_n >> 1) : p.block_n;
+      const int64_t n0 = (int64_t)n_tile * out_cols;
+      const bool has_add = (p.epi & (PB_EPI_RESIDUAL | PB_EPI_ROWBIAS)) != 0;
+      float4 add_cur[8], add_nxt[8];
+      auto fetch_add = [&](int c0, float4 (&dst)[8]) {
+        const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int64_t m = rows_m[i];
+          if (m >= 0 && b_col < cw) {
+            const int64_t n = n0 + c0 + b_col;
+            if (p.epi & PB_EPI_RESIDUAL) t = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n);
+            if (p.epi & PB_EPI_ROWBIAS) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(p.rowbias + (m / p.rb_rows) * p.ldrb + n));
+              t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+          }
+          dst[i] = t;
+        }
+      };
+      if (has_add) fetch_add(0, add_cur);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+      for (int c0 = 0; c0 < out_cols; c0 += EPI_CHUNK) {
+        const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;
+        const uint32_t buf = epi_base + (chunk_counter & 1u) * EPI_STAGE_BYTES;
+        ++chunk_counter;
+        if (has_add && c0 + EPI_CHUNK < out_cols) fetch_add(c0 + EPI_CHUNK, add_nxt);
+#pragma unroll
+        for (int h = 0; h < EPI_CHUNK; h += 16) {
+          if (h < cw) {
+            float v[16];
+            tmem_ld16(t_row + (uint32_t)(c0 + h), v);
+            float g[16];
+            if (GEGLU) tmem_ld16(t_row + (uint32_t)(out_cols + c0 + h), g);
+            tmem_ld_wait();
+            if (p.epi & PB_EPI_BIAS) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + h + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                if (GEGLU) {
+                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_half + n0 + c0 + h + j));
+                  g[j] += g4.x; g[j + 1] += g4.y; g[j + 2] += g4.z; g[j + 3] += g4.w;
+                }
+              }
+            }
+            if (GEGLU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] *= gelu_f(g[j]);
+            }
+            const uint32_t dst = buf + (uint32_t)(r * EPI_LD + h) * 4u;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 4u * j), "f"(v[j]), "f"(v[j + 1]),
+                           "f"(v[j + 2]), "f"(v[j + 3])
+                           : "memory");
+          }
+        }
+        if (c0 + EPI_CHUNK >= out_cols) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty_bar(acc));   // 4 warps x 2 CTAs free the accumulator pair
+        }
+        epi_bar_sync();
+        if (b_col < cw) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t m = rows_m[i];
+            if (m < 0) continue;
+            float4 val;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w)
+                         : "r"(buf + (uint32_t)((b_row0 + 16 * i) * EPI_LD + b_col) * 4u));
+            if (has_add) { val.x += add_cur[i].x; val.y += add_cur[i].y; val.z += add_cur[i].z; val.w += add_cur[i].w; }
+            const float o[4] = {val.x, val.y, val.z, val.w};
+            store4(C + m * p.ldc + n0 + c0 + b_col, o);
+          }
+        }
+        if (has_add) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) add_cur[i] = add_nxt[i];
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // nobody frees tensor memory / exits while the peer may still touch it
+  if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
 // split-K fold: C = sum_s partial[s] (+bias +rowbias +residual), deterministic order
 template <typename TC>
 __global__ void __launch_bounds__(256)
@@ -442,9 +719,29 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
   return PB_OK;
 }
 
+template <int MODE, bool GEGLU, typename TC>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, size_t smem, cudaStream_t st) {
+  static bool configured = false;
+  auto kern = tc_gemm_pair_kernel<MODE, GEGLU, TC>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_pair_kernel)");
+    configured = true;
+  }
+  int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  if (pairs > num_sms() / 2) pairs = num_sms() / 2;
+  kern<<<2 * pairs, NUM_THREADS, smem, st>>>(tmA, tmB, p);   // __cluster_dims__(2,1,1)
+  PB_LAUNCH_CHECK("tc_gemm_pair_kernel");
+  return PB_OK;
+}
+
 template <int MODE, bool GEGLU>
 static int launch_c(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, size_t smem, cudaStream_t st,
                     int c_dtype) {
+  if (p.pair) {
+    if (c_dtype == PB_F32) return launch_pair<MODE, GEGLU, float>(a, b, p, smem, st);
+    return launch_pair<MODE, GEGLU, bf16>(a, b, p, smem, st);
+  }
   if (c_dtype == PB_F32) return launch<MODE, GEGLU, float>(a, b, p, smem, st);
   return launch<MODE, GEGLU, bf16>(a, b, p, smem, st);
 }
@@ -541,14 +838,27 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     p.c = a->workspace; p.ldc = a->N; p.epi = 0;
     p.bias = nullptr; p.rowbias = nullptr; p.residual = nullptr;
   }
+  // CTA pairs whenever there are enough 256-row tiles to occupy the 74 SM pairs and no split-K
+  static const bool pair_enabled = []() { const char* e = getenv("PB_TC_PAIR"); return !(e && e[0] == '0'); }();
+  p.pair = 0;
+  if (pair_enabled && p.splits == 1 && p.m_tiles >= 2) {
+    const int pm = (p.m_tiles + 1) / 2;
+    const int bn_pair = pick_block_n(n_cols, geglu ? 128 : 256, 2 * pm);   // waves counted over 74 pairs ~ 148 / 2
+    if (bn_pair >= 32 && (long)pm * (n_cols / bn_pair) * 2 >= num_sms() / 2) {
+      p.pair = 1;
+      p.block_n = geglu ? 2 * bn_pair : bn_pair;
+      p.n_tiles = n_cols / bn_pair;
+    }
+  }
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t str[1] = {(uint64_t)a->K * esz};
-    uint32_t box[2] = {BLOCK_K, (uint32_t)(geglu ? p.block_n / 2 : p.block_n)};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)(p.block_n / 2)};
+    if (!p.pair && !geglu) box[1] = (uint32_t)p.block_n;
     rc = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box, nullptr);
     if (rc != PB_OK) return rc;
   }
-  const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = SMEM_PIPE_BUDGET / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 2 * EPI_STAGE_BYTES + BAR_BYTES;
