@@ -1,0 +1,87 @@
+"""GPU, BASELINE.json's full size (1.44 B-parameter U-Net, latent 4x16x40x64, context 333x1024):
+one forward against the CPU oracle in both precision modes, plus size-independent properties
+(determinism, batch consistency, CFG-step algebra) that need no oracle."""
+import pytest
+import torch
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full():
+    from pandora_b200 import UNetModel, config
+    from pandora_b200.synthetic import randomize_module_, synth_inputs
+    with torch.device("cuda"):
+        m = UNetModel(**config.UNET_512).eval()
+    randomize_module_(m, 1234)
+    inp = synth_inputs(1, config.LATENT_512, 1024, seed=0)
+    return m, inp
+
+
+def test_full_size_forward_matches_oracle_fp32_and_bf16(full):
+    from oracle import unet_oracle
+    from pandora_b200 import config
+    from pandora_b200.synthetic import synth_state_dict
+    m, inp = full
+    x = torch.cat([inp["x"], inp["c_concat"]], 1)
+    t = torch.tensor([499])
+    fs = torch.tensor([24])
+    sd = synth_state_dict(unet_oracle.unet_param_shapes(config.UNET_512), 1234)
+    ref = unet_oracle.unet_forward(sd, config.UNET_512, x, t, inp["context"], fs)
+    del sd
+    m.compute_mode = "fp32"
+    y32 = m(x.cuda(), t.cuda(), context=inp["context"].cuda(), fs=fs.cuda()).cpu()
+    e32 = rel_l2(y32, ref)
+    m.compute_mode = "bf16"
+    m.invalidate_packed_weights()
+    yb = m(x.cuda(), t.cuda(), context=inp["context"].cuda(), fs=fs.cuda()).cpu()
+    eb = rel_l2(yb, ref)
+    print(f"full size 16x320x512: fp32 mode rel-L2 = {e32:.3e}, bf16 mode rel-L2 = {eb:.3e}")
+    assert e32 < 1e-3 and eb < 2e-2
+
+
+def test_full_size_determinism_and_batch_consistency(full):
+    m, inp = full
+    m.compute_mode = "bf16"
+    x = inp["x"].cuda()
+    z = inp["c_concat"].cuda()
+    ctx = inp["context"].cuda()
+    t = torch.tensor([259], device="cuda")
+    y1 = m(x, t, context=ctx, x_concat=[z])
+    y2 = m(x, t, context=ctx, x_concat=[z])
+    assert torch.equal(y1, y2)
+    assert torch.isfinite(y1).all()
+    # a batch of two different samples == the two samples run alone
+    x2 = torch.cat([x, x.flip(3)], 0)
+    z2 = torch.cat([z, z.flip(4)], 0)
+    ctx2 = torch.cat([ctx, ctx.flip(1)], 0)
+    t2 = torch.tensor([259, 19], device="cuda")
+    yb = m(x2, t2, context=ctx2, x_concat=[z2])
+    ya = m(x2[1:], t2[1:], context=ctx2[1:].contiguous(), x_concat=[z2[1:]])
+    assert rel_l2(yb[0], y1[0]) < 1e-6 and rel_l2(yb[1], ya[0]) < 1e-6
+
+
+def test_full_size_cfg_step_algebra(full):
+    """With identical cond/uncond conditioning the CFG combine must be a no-op for any scale, and a full
+    graph-replayed step must equal the eager step."""
+    from pandora_b200 import DDIMSampler, LatentDiffusionLite, config
+    m, inp = full
+    m.compute_mode = "bf16"
+    model = LatentDiffusionLite(m, **config.DIFFUSION_512).cuda()
+    d = {k: v.cuda() for k, v in inp.items()}
+    cond = dict(c_crossattn=[d["context"]], c_concat=[d["c_concat"]])
+    outs = []
+    for graph in (False, True):
+        for scale in (1.0, 7.5):
+            s = DDIMSampler(model)
+            s.use_cuda_graph = graph
+            torch.manual_seed(3)
+            x, _ = s.sample(S=2, batch_size=1, shape=config.LATENT_512, conditioning=cond,
+                            unconditional_conditioning=cond, unconditional_guidance_scale=scale, eta=1.0,
+                            x_T=d["x"], verbose=False, timestep_spacing="uniform_trailing")
+            outs.append(x.float())
+    assert rel_l2(outs[1], outs[0]) < 1e-5      # CFG with uc == c is the identity
+    assert rel_l2(outs[2], outs[0]) < 1e-6      # graph replay == eager
+    assert rel_l2(outs[3], outs[1]) < 1e-6
