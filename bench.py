@@ -244,7 +244,7 @@ def main():
     # ---- e2e: public sampler objects, host (pinned) buffers, H2D/D2H inside the timed region
     host = {k: inp[k].pin_memory() for k in ("x", "c_concat", "context", "uc_context")}
     host["noise"] = torch.randn(shape).pin_memory()
-    host["ts"] = torch.zeros(b, dtype=torch.long).pin_memory()
+    host["ts"] = torch.zeros(g.ts.shape[0], dtype=torch.long).pin_memory()
     host_out = torch.empty(shape).pin_memory()
     h2d = sum(host[k].numel() * host[k].element_size() for k in host)
     d2h = host_out.numel() * host_out.element_size()

@@ -99,15 +99,15 @@ def profile_end():
     global _prof
     items, _prof = _prof or [], None
     torch.cuda.synchronize()
-    return [dict(name=n, flops=f, bytes=b, ms=e0.elapsed_time(e1)) for (n, f, b, e0, e1) in items]
+    return [dict(name=n, flops=f, bytes=b, detail=d, ms=e0.elapsed_time(e1)) for (n, f, b, d, e0, e1) in items]
 
 
-def _tick(name, flops=0, nbytes=0):
+def _tick(name, flops=0, nbytes=0, detail=""):
     if _prof is None:
         return None
     e0 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    return (name, flops, nbytes, e0)
+    return (name, flops, nbytes, detail() if callable(detail) else detail, e0)
 
 
 def _tock(tok):
@@ -222,7 +222,9 @@ def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=
             ws = torch.empty(nb, dtype=torch.uint8, device=a.device)
             g.workspace, g.workspace_bytes = ws.data_ptr(), nb
     tok = _tick(("tc_" if tc else "simt_") + ("gemm", "conv3x3", "convt3")[mode] + ("_geglu" if geglu else ""),
-                2 * g.M * g.N * g.K, (g.M * g.K // (1, 9, 3)[mode] + g.N * g.K) * a.element_size() + _nbytes(c, residual))
+                2 * g.M * g.N * g.K, (g.M * g.K // (1, 9, 3)[mode] + g.N * g.K) * a.element_size() + _nbytes(c, residual),
+                lambda: f"M{g.M} N{g.N} K{g.K} epi{epi} out{'f32' if g.c_dtype == F32 else 'bf16'}"
+                        + (f" s{g.stride}" if mode == A_CONV3X3 and g.stride != 1 else ""))
     rc = fn(C.byref(g), _stream())
     if rc == E_UNSUPPORTED and tc:
         return False
@@ -243,7 +245,7 @@ def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32):
     xp, ldx = _rows(x)
     yp, ldy = _rows(y)
     st = _stream()
-    tok = _tick("groupnorm", 0, 2 * _nbytes(x) + _nbytes(y))
+    tok = _tick("groupnorm", 0, 2 * _nbytes(x) + _nbytes(y), f"inst{n_inst} rows{rows_per_inst} C{Cc}")
     _check(lib.pb_groupnorm_stats(xp, dt(x), ldx, n_inst, rows_per_inst, Cc, groups, eps, gamma.data_ptr(),
                                   beta.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes, st),
            "pb_groupnorm_stats")
@@ -280,7 +282,7 @@ def layernorm(x, y, gamma, beta, eps=1e-5):
     global launches
     xp, ldx = _rows(x)
     yp, ldy = _rows(y)
-    tok = _tick("layernorm", 0, _nbytes(x, y))
+    tok = _tick("layernorm", 0, _nbytes(x, y), f"rows{x.shape[0]} C{x.shape[1]}")
     _check(load().pb_layernorm(xp, dt(x), ldx, yp, dt(y), ldy, x.shape[0], x.shape[1],
                                gamma.data_ptr(), beta.data_ptr(), eps, _stream()), "pb_layernorm")
     _tock(tok)
@@ -308,7 +310,7 @@ def attention(q, k, v, out, o_addr, batch, heads, n_q, n_kv, scale, dtype, accum
     esz = 2 if dtype == BF16 else 4
     kind = "temporal" if n_q <= 32 else ("self" if n_q == n_kv else "cross")
     tok = _tick(("tc_" if tc else "simt_") + "attn_" + kind, 4 * batch * heads * n_q * n_kv * 64,
-                batch * heads * 64 * esz * (2 * n_q + 2 * n_kv))
+                batch * heads * 64 * esz * (2 * n_q + 2 * n_kv), f"B{batch} h{heads} nq{n_q} nkv{n_kv}")
     rc = fn(C.byref(a), _stream())
     if rc == E_UNSUPPORTED and tc:
         return False
@@ -344,7 +346,7 @@ def copy_rows(src, dst):
     global launches
     sp, lds = _rows(src)
     dp, ldd = _rows(dst)
-    tok = _tick("copy_rows", 0, _nbytes(src, dst))
+    tok = _tick("copy_rows", 0, _nbytes(src, dst), f"rows{src.shape[0]} C{src.shape[1]} {src.dtype}->{dst.dtype}")
     _check(load().pb_copy_rows(sp, dt(src), lds, dp, dt(dst), ldd, src.shape[0], src.shape[1], _stream()),
            "pb_copy_rows")
     _tock(tok)

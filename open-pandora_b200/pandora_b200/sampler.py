@@ -88,7 +88,13 @@ class GraphedCFGStep:
 
     The conditioning (cross-attention context, c_concat) is read from the tensors given at construction;
     `refresh_conditioning()` must be called after their contents change (it recomputes the cached K/V
-    projections in place so the captured graph sees them)."""
+    projections in place so the captured graph sees them).
+
+    The two CFG branches (ddim.py:233-234: two sequential `apply_model` calls on the same x) run as ONE
+    U-Net forward over a batch of 2b — rows [0, b) carry the conditional, rows [b, 2b) the unconditional
+    conditioning — unless the branches are split across ranks (`cfg_parallel`) or the clip is
+    sequence-parallel (batch 1 per rank).  Every operator of the U-Net is per-sample, so this is the same
+    arithmetic with half the launches and twice the rows per GEMM."""
 
     def __init__(self, sampler, unet, shape, cond, uncond, fs, cfg_scale, guidance_rescale, temperature, table):
         dev = sampler.model.device
@@ -109,12 +115,28 @@ class GraphedCFGStep:
         self.ctx_u = self.z_u = None
         if self.cfg:
             self.ctx_u, self.z_u = cat(uncond["c_crossattn"]), cat(uncond["c_concat"])
+        self.batched = (self.cfg and sampler.batch_cfg and sampler.cfg_parallel is None
+                        and getattr(unet, "sequence_parallel", None) is None)
+        if self.batched:
+            b = shape[0]
+            self.x2 = torch.zeros((2 * b, *shape[1:]), dtype=f32, device=dev)
+            self.ts = torch.zeros((2 * b,), dtype=torch.long, device=dev)
+            self.ctx_b = torch.cat([self.ctx_c, self.ctx_u], 0).contiguous()
+            self.z_b = torch.cat([self.z_c, self.z_u], 0).contiguous()
+            self.fs_b = None if fs is None else torch.cat([fs, fs], 0)
         self.graph = None
         self.launches_per_step = 0
 
     def _body(self):
         cfgp = self.sampler.cfg_parallel if self.cfg else None
-        if cfgp is not None:                   # one branch per rank, then all-gather v
+        if self.batched:                       # both branches in one forward over 2b samples
+            b = self.x.shape[0]
+            flat = self.x.view(b, -1)
+            abi.copy_rows(flat, self.x2.view(2 * b, -1)[:b])
+            abi.copy_rows(flat, self.x2.view(2 * b, -1)[b:])
+            v = self.unet(self.x2, self.ts, context=self.ctx_b, fs=self.fs_b, x_concat=[self.z_b])
+            v_c, v_u = v[:b], v[b:]
+        elif cfgp is not None:                 # one branch per rank, then all-gather v
             ctx, z = cfgp.my_branch((self.ctx_c, self.z_c), (self.ctx_u, self.z_u))
             v_c, v_u = cfgp.exchange(self.unet(self.x, self.ts, context=ctx, fs=self.fs, x_concat=[z]))
         else:
@@ -141,6 +163,12 @@ class GraphedCFGStep:
         self.step_index.zero_()
 
     def refresh_conditioning(self):
+        if self.batched:
+            b = self.x.shape[0]
+            self.ctx_b[:b].copy_(self.ctx_c); self.ctx_b[b:].copy_(self.ctx_u)
+            self.z_b[:b].copy_(self.z_c); self.z_b[b:].copy_(self.z_u)
+            self.unet.refresh_context(self.ctx_b, self.x.shape[2])
+            return
         for ctx in (self.ctx_c, self.ctx_u):
             if ctx is not None:
                 self.unet.refresh_context(ctx, self.x.shape[2])
@@ -169,6 +197,10 @@ class DDIMSampler(object):
         self._tables = {}
         #: capture the CFG step as a CUDA graph when the native U-Net is underneath (set False to run eagerly)
         self.use_cuda_graph = True
+        #: run the cond / uncond branches of a CFG step as one U-Net forward over a doubled batch (same arithmetic
+        #: per sample; False = two sequential forwards exactly like ddim.py:233-234)
+        self.batch_cfg = True
+        self._cfg_cat = None
         #: `pandora_b200.dist.CFGParallel`: evaluate the cond / uncond branches on two ranks (one all-gather of v
         #: per step); None = both branches on this rank
         self.cfg_parallel = None
@@ -389,6 +421,36 @@ class DDIMSampler(object):
             return unet(x, t, context=cc, x_concat=list(c["c_concat"]), **kwargs)
         return m.apply_model(x, t, c, **kwargs)
 
+    def _native_unet(self):
+        inner = getattr(self.model, "model", None)
+        unet = getattr(inner, "diffusion_model", None)
+        if isinstance(unet, UNetModel) and getattr(inner, "conditioning_key", None) == "hybrid":
+            return unet
+        return None
+
+    def _can_batch_cfg(self, c, uc):
+        unet = self._native_unet()
+        return (self.batch_cfg and unet is not None and unet.sequence_parallel is None
+                and isinstance(c, dict) and isinstance(uc, dict))
+
+    def _denoise_cfg_batched(self, x32, t, c, uc, **kwargs):
+        """Both CFG branches as one forward over 2b samples (rows [0,b) cond, [b,2b) uncond).  The concatenated
+        conditioning is cached per (cond, uncond) tensor identity so the U-Net's context K/V cache keeps hitting."""
+        cat = lambda ts: ts[0] if len(ts) == 1 else torch.cat(list(ts), 1)
+        srcs = (cat(c["c_crossattn"]), cat(uc["c_crossattn"]), cat(c["c_concat"]), cat(uc["c_concat"]))
+        key = tuple((s.data_ptr(), s._version, tuple(s.shape)) for s in srcs)
+        if self._cfg_cat is None or self._cfg_cat[0] != key:
+            self._cfg_cat = (key, torch.cat(srcs[:2], 0).contiguous(), torch.cat(srcs[2:], 0).contiguous(), srcs)
+        _, ctx_b, z_b, _ = self._cfg_cat
+        b = x32.shape[0]
+        kw = dict(kwargs)
+        fs = kw.get("fs")
+        if isinstance(fs, torch.Tensor) and fs.dim() and fs.shape[0] == b:
+            kw["fs"] = torch.cat([fs, fs], 0)
+        v = self._native_unet()(torch.cat([x32, x32], 0), torch.cat([t, t], 0), context=ctx_b, x_concat=[z_b], **kw)
+        v = v.float()
+        return v[:b].contiguous(), v[b:].contiguous()
+
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False,
                       quantize_denoised=False, temperature=1., noise_dropout=0., score_corrector=None,
@@ -409,6 +471,8 @@ class DDIMSampler(object):
         if cfg and self.cfg_parallel is not None:
             mine = self.cfg_parallel.my_branch(c, unconditional_conditioning)
             v_c, v_u = self.cfg_parallel.exchange(self._denoise(x32, t, mine, **kwargs).float().contiguous())
+        elif cfg and self._can_batch_cfg(c, unconditional_conditioning):
+            v_c, v_u = self._denoise_cfg_batched(x32, t, c, unconditional_conditioning, **kwargs)
         else:
             v_c = self._denoise(x32, t, c, **kwargs).float().contiguous()
             if cfg:
