@@ -2,22 +2,29 @@
 //
 //   C[m, n] = epilogue( sum_k A[m, k] * W[n, k] )      A, W bf16; fp32 accumulation in tensor memory
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0      TMA producer   : cp.async.bulk.tensor tiles of A (128 rows x 64 k) and W (block_n x 64 k)
 //                                into a ring of 128B-swizzled shared-memory stages (mbarrier full/empty)
 //   warp 1      MMA issuer     : one elected thread issues tcgen05.mma (M=128, N=block_n, K=16) x4 per
 //                                stage; tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2..5  epilogue       : tcgen05.ld the 128 x block_n fp32 accumulator in 32-column chunks (thread =
-//                                row), + bias / GEGLU, transpose through a padded shared-memory stage, then
-//                                row-contiguous (coalesced) row-bias / residual loads and stores
+//   warps 2..9  epilogue       : two teams of four warps (a team covers the four TMEM lane quarters); a team
+//                                takes every other 32-column chunk of the 128 x block_n fp32 accumulator:
+//                                tcgen05.ld (thread = row) -> +bias / GEGLU / +row-bias / +residual -> swizzled
+//                                shared-memory slot -> ONE bulk tensor store per chunk.  The residual tile
+//                                is fetched by a bulk tensor LOAD into the same slot one chunk ahead, so the
+//                                epilogue issues no per-thread global loads or stores at all: the K=320
+//                                layers are bound by HBM, and memory-level parallelism comes from the copy
+//                                engine instead of 128 threads x 8 loads.
 // The accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the
 // MMAs of tile i+1.
 //
-// The A operand is addressed purely by TMA coordinates, so convolution needs no im2col buffer:
-//   LINEAR   2-D map [M][K]
-//   CONV3X3  4-D map [n][y][x][c]; tap (ky,kx) = the same box shifted by (ky-1, kx-1); out-of-bounds
+// The A operand and the C / residual tiles are addressed purely by TMA coordinates, so convolution needs
+// no im2col buffer and no row-index arithmetic:
+//   LINEAR   A: 2-D map [M][K]                       C: [splits][M][N]
+//   CONV3X3  A: 4-D map [n][y][x][c]; tap (ky,kx) = the same box shifted by (ky-1, kx-1); out-of-bounds
 //            rows/columns are zero-filled by the TMA unit, which IS the conv's zero padding
-//   CONVT3   4-D map [b][t][p][c]; tap kt = box shifted by kt-1 frames (zero-filled outside the clip)
+//                                                    C: [n][y][x][cout], same brick
+//   CONVT3   A: 4-D map [b][t][p][c]; tap kt = box shifted by kt-1 frames (zero-filled outside the clip)
 // A 128-row tile is a BW x BH x BN (x, y, image) or BP x BT (pixel, frame) brick chosen so the brick tiles
 // the tensor exactly.
 #include <stdlib.h>
@@ -32,22 +39,21 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                        // two teams of four
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;    // 320
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_CHUNK = 32;                           // accumulator columns per epilogue chunk
-constexpr int EPI_LD = EPI_CHUNK + 4;                   // padded row (floats): conflict-free v4 access
-constexpr int EPI_STAGE_BYTES = BLOCK_M * EPI_LD * 4;   // 18 KiB, x2 buffers
-constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 4) + 16;
+constexpr int EPI_SLOTS = 2;                            // staging slots per team
+constexpr int EPI_SLOT_F32 = BLOCK_M * EPI_CHUNK * 4;   // 16 KiB: [128][32] fp32, 128B-swizzled rows
+constexpr int EPI_SLOT_BF16 = BLOCK_M * EPI_CHUNK * 2;  //  8 KiB: [128][32] bf16,  64B-swizzled rows
+constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 4 + 2 * EPI_SLOTS) + 16;
 constexpr int SMEM_TOTAL = 227 * 1024;
-constexpr int SMEM_PIPE_BUDGET = SMEM_TOTAL - 1024 - 2 * EPI_STAGE_BYTES - BAR_BYTES;
 
 struct TcParams {
-  void* c;
   const float* bias;
   const float* rowbias;
-  const float* residual;
-  int64_t M, ldc, ldr, ldrb, rb_rows;
+  int64_t M, ldrb, rb_rows;
   int N;                 // accumulator columns in total (weight rows)
   int block_n;           // accumulator columns per tile
   int n_tiles, m_tiles;
@@ -56,14 +62,15 @@ struct TcParams {
   int stages;
   int epi;
   int geglu_half;        // N / 2 when GEGLU
+  int slot_bytes;        // epilogue staging slot size
   // brick geometry (conv modes)
   int bw, bh, bn_img;    // CONV3X3: brick x, y, images ; CONVT3: bw = pixels, bh = frames
   int W, H;              // CONV3X3: image size ; CONVT3: W = HW (pixels per frame), H = T
   int tiles_x, tiles_y;  // CONV3X3: W/bw, H/bh ; CONVT3: HW/bw, T/bh
+  int n_outer;           // images (CONV3X3) / samples (CONVT3): the C map's outermost extent per split
   int cstride;           // CONV3X3 spatial stride (1 or 2); W/H above are OUTPUT sizes
   int splits;            // split-K ways (1 = off); split s covers k-iterations [s*kps, (s+1)*kps)
   int kps;               // k-iterations per split
-  int64_t split_stride;  // elements between the partial outputs of consecutive splits
   int pair;              // 1 = CTA-pair kernel (cta_group::2): block_n is the width of the 256-row pair tile
 };
 
@@ -80,24 +87,240 @@ __device__ __forceinline__ int64_t out_row(const TcParams& p, int m_tile, int r)
   return ((int64_t)(tn * p.bn_img + bi) * p.H + (ty * p.bh + by)) * p.W + (tx * p.bw + bx);
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// ---- bulk tensor store / group management (epilogue)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void team_bar_sync(int team) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + team) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// erf GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 7 FMA.
+// Only used where the result is rounded to bf16 (relative 4e-3) right away.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = poly * t * __expf(-z * z);       // 1 - erf(z)
+  const float erf_abs = 1.0f - e;
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
+// ================================================================================================ epilogue
+// Runs in warps 2..9.  first/step/total describe this CTA's work list (tiles x splits, or pair tiles);
+// `rank` is the CTA rank inside a pair (0 otherwise).  tempty_addr(acc) is the (possibly remote) barrier
+// that hands the accumulator buffer back to the MMA issuer.
+template <int MODE, bool GEGLU, typename TC, bool PAIR>
+__device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUtensorMap* tmR, const TcParams& p,
+                                              uint32_t tmem_base, uint32_t epi_base, uint32_t tfull0, uint32_t tempty0,
+                                              uint32_t rfull0, int first, int step, int total, int rank) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = (warp - 2) >> 2;
+  const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+  const int r = quarter * 32 + lane;       // accumulator row owned by this thread
+  const bool leader = (warp - 2) == team * 4 && lane == 0;
+  const bool RES = (p.epi & PB_EPI_RESIDUAL) != 0;
+  constexpr bool OUT_BF16 = sizeof(TC) == 2;
+  const int out_cols = GEGLU ? (p.block_n >> 1) : p.block_n;
+  const int n_chunks = (out_cols + EPI_CHUNK - 1) / EPI_CHUNK;
+  const uint32_t slot_base = epi_base + (uint32_t)(team * EPI_SLOTS * p.slot_bytes);
+  auto rfull = [&](int slot) { return rfull0 + 8u * (uint32_t)(team * EPI_SLOTS + slot); };
+
+  // (work, chunk) -> tensor coordinates of the 128 x 32 output box
+  auto coords = [&](int work, int ci, int (&c)[4], int& m_tile, int& n_tile) {
+    int split = 0;
+    if (PAIR) {
+      n_tile = work % p.n_tiles;
+      m_tile = 2 * (work / p.n_tiles) + rank;
+    } else {
+      const int tile = work / p.splits;
+      split = work - tile * p.splits;
+      n_tile = tile % p.n_tiles;
+      m_tile = tile / p.n_tiles;
+    }
+    c[0] = n_tile * out_cols + ci * EPI_CHUNK;
+    if (MODE == PB_A_LINEAR) {
+      c[1] = m_tile * BLOCK_M; c[2] = split; c[3] = 0;
+    } else {
+      c[1] = (m_tile % p.tiles_x) * p.bw;
+      c[2] = ((m_tile / p.tiles_x) % p.tiles_y) * p.bh;
+      c[3] = (m_tile / (p.tiles_x * p.tiles_y)) * p.bn_img + split * p.n_outer;
+    }
+  };
+
+  int acc = 0, acc_phase = 0;
+  uint32_t cnt = 0;          // chunks this team has processed: slot = cnt % SLOTS, parity = (cnt / SLOTS) & 1
+  if (RES && leader && first < total && team < n_chunks) {
+    int c[4], mt, nt;
+    coords(first, team, c, mt, nt);
+    mbar_expect_tx(rfull(0), (uint32_t)EPI_SLOT_F32);
+    tma_load_4d(slot_base, tmR, rfull(0), c[0], c[1], c[2], c[3]);
+  }
+  for (int work = first; work < total; work += step) {
+    int c[4], m_tile, n_tile;
+    coords(work, 0, c, m_tile, n_tile);
+    const int64_t n0 = (int64_t)n_tile * out_cols;       // first output column of the tile
+    const float* rb_ptr = nullptr;
+    if (p.epi & PB_EPI_ROWBIAS) {
+      int64_t m = out_row<MODE>(p, m_tile, r);
+      if (m >= p.M) m = p.M - 1;
+      rb_ptr = p.rowbias + (m / p.rb_rows) * p.ldrb + n0;
+    }
+    mbar_wait(tfull0 + 8u * acc, acc_phase);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+    for (int ci = team; ci < n_chunks; ci += 2) {
+      const int c0 = ci * EPI_CHUNK;
+      const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;   // 32, or 16 on a ragged last chunk
+      const int slot = cnt % EPI_SLOTS;
+      const uint32_t sphase = (cnt / EPI_SLOTS) & 1u;
+      const uint32_t sbuf = slot_base + (uint32_t)(slot * p.slot_bytes);
+      // ---- (1) TMEM -> registers (+bias, GEGLU)
+      float v[EPI_CHUNK];
+#pragma unroll
+      for (int h = 0; h < EPI_CHUNK; h += 16) {
+        if (h < cw) {
+          float a16[16];
+          tmem_ld16(t_row + (uint32_t)(c0 + h), a16);
+          float g16[16];
+          if (GEGLU) tmem_ld16(t_row + (uint32_t)(out_cols + c0 + h), g16);
+          tmem_ld_wait();
+          if (p.epi & PB_EPI_BIAS) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + h + j));
+              a16[j] += b4.x; a16[j + 1] += b4.y; a16[j + 2] += b4.z; a16[j + 3] += b4.w;
+              if (GEGLU) {
+                const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_half + n0 + c0 + h + j));
+                g16[j] += g4.x; g16[j + 1] += g4.y; g16[j + 2] += g4.z; g16[j + 3] += g4.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[h + j] = GEGLU ? a16[j] * gelu_fast(g16[j]) : a16[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[h + j] = 0.f;
+        }
+      }
+      if (ci + 2 >= n_chunks) {
+        // this team's last read of the accumulator buffer: hand it back to the MMA warp early
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((tempty0 + 8u * acc) & 0xFEFFFFFFu) : "memory");
+          else mbar_arrive(tempty0 + 8u * acc);
+        }
+      }
+      if (rb_ptr != nullptr) {
+#pragma unroll
+        for (int j = 0; j < EPI_CHUNK; j += 4) {
+          if (j < cw) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(rb_ptr + c0 + j));
+            v[j] += u.x; v[j + 1] += u.y; v[j + 2] += u.z; v[j + 3] += u.w;
+          }
+        }
+      }
+      // ---- (2) the slot is free (no residual) / holds the residual tile (bulk load issued one chunk ago)
+      if (RES) {
+        mbar_wait(rfull(slot), sphase);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t4[4];
+          lds128(sbuf + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)), t4);
+          v[4 * j] += t4[0]; v[4 * j + 1] += t4[1]; v[4 * j + 2] += t4[2]; v[4 * j + 3] += t4[3];
+        }
+        if (OUT_BF16) team_bar_sync(team);   // rows are repacked to 64 B: all reads before any write
+      } else {
+        if (leader) bulk_wait_read<EPI_SLOTS - 1>();
+        team_bar_sync(team);
+      }
+      // ---- (3) registers -> swizzled staging slot
+      if (OUT_BF16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128u(sbuf + (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)), pack2_bf16(v[8 * j], v[8 * j + 1]),
+                  pack2_bf16(v[8 * j + 2], v[8 * j + 3]), pack2_bf16(v[8 * j + 4], v[8 * j + 5]),
+                  pack2_bf16(v[8 * j + 6], v[8 * j + 7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(sbuf + (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      // ---- (4) one bulk tensor store per chunk; prefetch the residual of this team's next chunk
+      fence_proxy_async();
+      team_bar_sync(team);
+      if (leader) {
+        coords(work, ci, c, m_tile, n_tile);
+        tma_store_4d(tmC, sbuf, c[0], c[1], c[2], c[3]);
+        bulk_commit();
+        if (RES) {
+          int nwork = work, nci = ci + 2;
+          if (nci >= n_chunks) { nci = team; nwork += step; }
+          if (nwork < total) {
+            const int nslot = (cnt + 1) % EPI_SLOTS;
+            bulk_wait_read<EPI_SLOTS - 1>();       // the store that last used that slot has drained it
+            int nc[4], nmt, nnt;
+            coords(nwork, nci, nc, nmt, nnt);
+            mbar_expect_tx(rfull(nslot), (uint32_t)EPI_SLOT_F32);
+            tma_load_4d(slot_base + (uint32_t)(nslot * p.slot_bytes), tmR, rfull(nslot), nc[0], nc[1], nc[2], nc[3]);
+          }
+        }
+      }
+      ++cnt;
+    }
+    if (team >= n_chunks) {      // single-chunk tiles: the idle team still frees the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"((tempty0 + 8u * acc) & 0xFEFFFFFFu) : "memory");
+        else mbar_arrive(tempty0 + 8u * acc);
+      }
+    }
+    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+  }
+  if (leader) bulk_wait_all();     // shared memory must outlive the last bulk stores
+}
 
 template <int MODE, bool GEGLU, typename TC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // manual 1024-byte alignment (swizzle-128B atoms)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_stage_bytes = p.block_n * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  const uint32_t epi_base = smem_base + p.stages * stage_bytes;          // 2 x [128][EPI_LD] fp32
-  const uint32_t bar_base = epi_base + 2 * EPI_STAGE_BYTES;
-  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2]; then the TMEM base slot
+  const uint32_t epi_base = smem_base + p.stages * stage_bytes;          // 2 teams x EPI_SLOTS staging slots
+  const uint32_t bar_base = epi_base + 2 * EPI_SLOTS * p.slot_bytes;
+  // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], rfull[2*SLOTS]; then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t rfull0 = bar_base + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + 2 * EPI_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -106,8 +329,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+    if (p.epi & PB_EPI_RESIDUAL) prefetch_tmap(&tmR);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
+    for (int s = 0; s < 2 * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -190,118 +416,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ================================================================== epilogue (warps 2..5)
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
-    const int r = quarter * 32 + lane;       // accumulator row owned by this thread in phase A
-    const int et = threadIdx.x - 64;         // 0..127
-    const int b_row0 = et >> 3;              // phase B: rows b_row0 + 16*i, 4 columns at b_col
-    const int b_col = (et & 7) * 4;
-    int acc = 0, acc_phase = 0;
-    uint32_t chunk_counter = 0;
-    for (int work = blockIdx.x; work < total_tiles * p.splits; work += gridDim.x) {
-      const int tile = work / p.splits, split = work - tile * p.splits;
-      TC* C = reinterpret_cast<TC*>(p.c) + (int64_t)split * p.split_stride;   // split-K: partials, reduced afterwards
-      const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
-      // rows this thread stores in phase B (fixed for the tile)
-      int64_t rows_m[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t m = out_row<MODE>(p, m_tile, b_row0 + 16 * i);
-        rows_m[i] = m < p.M ? m : -1;
-      }
-      const int out_cols = GEGLU ? (p.block_n >> 1) : p.block_n;
-      const int64_t n0 = (int64_t)n_tile * out_cols;       // first output column of the tile
-      // residual + row-bias of a chunk are fetched one chunk ahead (registers), so their L2/HBM latency hides
-      // behind the TMEM drain and the barrier instead of being exposed after it
-      const bool has_add = (p.epi & (PB_EPI_RESIDUAL | PB_EPI_ROWBIAS)) != 0;
-      float4 add_cur[8], add_nxt[8];
-      auto fetch_add = [&](int c0, float4 (&dst)[8]) {
-        const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int64_t m = rows_m[i];
-          if (m >= 0 && b_col < cw) {
-            const int64_t n = n0 + c0 + b_col;
-            if (p.epi & PB_EPI_RESIDUAL) t = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n);
-            if (p.epi & PB_EPI_ROWBIAS) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(p.rowbias + (m / p.rb_rows) * p.ldrb + n));
-              t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-            }
-          }
-          dst[i] = t;
-        }
-      };
-      if (has_add) fetch_add(0, add_cur);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-      for (int c0 = 0; c0 < out_cols; c0 += EPI_CHUNK) {
-        const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;   // 16 or 32
-        const uint32_t buf = epi_base + (chunk_counter & 1u) * EPI_STAGE_BYTES;
-        ++chunk_counter;
-        if (has_add && c0 + EPI_CHUNK < out_cols) fetch_add(c0 + EPI_CHUNK, add_nxt);
-        // ---- phase A: TMEM -> registers (+bias, GEGLU) -> padded smem stage, thread = row
-#pragma unroll
-        for (int h = 0; h < EPI_CHUNK; h += 16) {
-          if (h < cw) {
-            float v[16];
-            tmem_ld16(t_row + (uint32_t)(c0 + h), v);
-            float g[16];
-            if (GEGLU) tmem_ld16(t_row + (uint32_t)(out_cols + c0 + h), g);
-            tmem_ld_wait();
-            if (p.epi & PB_EPI_BIAS) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + h + j));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                if (GEGLU) {
-                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_half + n0 + c0 + h + j));
-                  g[j] += g4.x; g[j + 1] += g4.y; g[j + 2] += g4.z; g[j + 3] += g4.w;
-                }
-              }
-            }
-            if (GEGLU) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] *= gelu_f(g[j]);
-            }
-            const uint32_t dst = buf + (uint32_t)(r * EPI_LD + h) * 4u;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 4u * j), "f"(v[j]), "f"(v[j + 1]),
-                           "f"(v[j + 2]), "f"(v[j + 3])
-                           : "memory");
-          }
-        }
-        if (c0 + EPI_CHUNK >= out_cols) {
-          // last chunk read: the accumulator buffer is drained, hand it back to the MMA warp early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
-        epi_bar_sync();   // stage written by all 128 epilogue threads (also orders reuse of the other buffer)
-        // ---- phase B: row-contiguous: 8 lanes x 16 B cover one 128-byte row segment
-        if (b_col < cw) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int64_t m = rows_m[i];
-            if (m < 0) continue;
-            float4 val;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w)
-                         : "r"(buf + (uint32_t)((b_row0 + 16 * i) * EPI_LD + b_col) * 4u));
-            if (has_add) { val.x += add_cur[i].x; val.y += add_cur[i].y; val.z += add_cur[i].z; val.w += add_cur[i].w; }
-            const float o[4] = {val.x, val.y, val.z, val.w};
-            store4(C + m * p.ldc + n0 + c0 + b_col, o);
-          }
-        }
-        if (has_add) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) add_cur[i] = add_nxt[i];
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    epilogue_loop<MODE, GEGLU, TC, false>(&tmC, &tmR, p, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), rfull0,
+                                          (int)blockIdx.x, (int)gridDim.x, total_tiles * p.splits, 0);
   }
 
   tc_fence_before();
@@ -354,9 +470,6 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {   // arrives on
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
-}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }
@@ -369,18 +482,20 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 
 template <int MODE, bool GEGLU, typename TC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int half_n = p.block_n >> 1;                        // W rows staged by this CTA
   const int stage_bytes = A_STAGE_BYTES + half_n * BLOCK_K * 2;
   const uint32_t epi_base = smem_base + p.stages * stage_bytes;
-  const uint32_t bar_base = epi_base + 2 * EPI_STAGE_BYTES;
+  const uint32_t bar_base = epi_base + 2 * EPI_SLOTS * p.slot_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // used in the leader only
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };       // one per CTA (multicast commit)
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };   // one per CTA (multicast commit)
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };  // leader only, 8 arrivals
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };  // leader only, 16 arrivals
+  const uint32_t rfull0 = bar_base + 8u * (2 * MAX_STAGES + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + 2 * EPI_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -393,8 +508,11 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
+    if (p.epi & PB_EPI_RESIDUAL) prefetch_tmap(&tmR);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS); }
+    for (int s = 0; s < 2 * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -470,112 +588,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ================================================================== epilogue (warps 2..5, both CTAs)
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const int et = threadIdx.x - 64;
-    const int b_row0 = et >> 3;
-    const int b_col = (et & 7) * 4;
-    TC* C = reinterpret_cast<TC*>(p.c);
-    int acc = 0, acc_phase = 0;
-    uint32_t chunk_counter = 0;
-    for (int work = pair_id; work < total_work; work += num_pairs) {
-      const int n_tile = work % p.n_tiles;
-      const int m_tile = 2 * (work / p.n_tiles) + (int)rank;
-      int64_t rows_m[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t m = m_tile < p.m_tiles ? out_row<MODE>(p, m_tile, b_row0 + 16 * i) : p.M;
-        rows_m[i] = m < p.M ? m : -1;
-      }
-      const int out_cols = GEGLU ? (p.block_n >> 1) : p.block_n;
-      const int64_t n0 = (int64_t)n_tile * out_cols;
-      const bool has_add = (p.epi & (PB_EPI_RESIDUAL | PB_EPI_ROWBIAS)) != 0;
-      float4 add_cur[8], add_nxt[8];
-      auto fetch_add = [&](int c0, float4 (&dst)[8]) {
-        const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int64_t m = rows_m[i];
-          if (m >= 0 && b_col < cw) {
-            const int64_t n = n0 + c0 + b_col;
-            if (p.epi & PB_EPI_RESIDUAL) t = *reinterpret_cast<const float4*>(p.residual + m * p.ldr + n);
-            if (p.epi & PB_EPI_ROWBIAS) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(p.rowbias + (m / p.rb_rows) * p.ldrb + n));
-              t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-            }
-          }
-          dst[i] = t;
-        }
-      };
-      if (has_add) fetch_add(0, add_cur);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-      for (int c0 = 0; c0 < out_cols; c0 += EPI_CHUNK) {
-        const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;
-        const uint32_t buf = epi_base + (chunk_counter & 1u) * EPI_STAGE_BYTES;
-        ++chunk_counter;
-        if (has_add && c0 + EPI_CHUNK < out_cols) fetch_add(c0 + EPI_CHUNK, add_nxt);
-#pragma unroll
-        for (int h = 0; h < EPI_CHUNK; h += 16) {
-          if (h < cw) {
-            float v[16];
-            tmem_ld16(t_row + (uint32_t)(c0 + h), v);
-            float g[16];
-            if (GEGLU) tmem_ld16(t_row + (uint32_t)(out_cols + c0 + h), g);
-            tmem_ld_wait();
-            if (p.epi & PB_EPI_BIAS) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + h + j));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                if (GEGLU) {
-                  const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.bias + p.geglu_half + n0 + c0 + h + j));
-                  g[j] += g4.x; g[j + 1] += g4.y; g[j + 2] += g4.z; g[j + 3] += g4.w;
-                }
-              }
-            }
-            if (GEGLU) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] *= gelu_f(g[j]);
-            }
-            const uint32_t dst = buf + (uint32_t)(r * EPI_LD + h) * 4u;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 4u * j), "f"(v[j]), "f"(v[j + 1]),
-                           "f"(v[j + 2]), "f"(v[j + 3])
-                           : "memory");
-          }
-        }
-        if (c0 + EPI_CHUNK >= out_cols) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(tempty_bar(acc));   // 4 warps x 2 CTAs free the accumulator pair
-        }
-        epi_bar_sync();
-        if (b_col < cw) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int64_t m = rows_m[i];
-            if (m < 0) continue;
-            float4 val;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(val.x), "=f"(val.y), "=f"(val.z), "=f"(val.w)
-                         : "r"(buf + (uint32_t)((b_row0 + 16 * i) * EPI_LD + b_col) * 4u));
-            if (has_add) { val.x += add_cur[i].x; val.y += add_cur[i].y; val.z += add_cur[i].z; val.w += add_cur[i].w; }
-            const float o[4] = {val.x, val.y, val.z, val.w};
-            store4(C + m * p.ldc + n0 + c0 + b_col, o);
-          }
-        }
-        if (has_add) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) add_cur[i] = add_nxt[i];
-        }
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
+    // ================================================================== epilogue (warps 2..9, both CTAs)
+    epilogue_loop<MODE, GEGLU, TC, true>(&tmC, &tmR, p, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), rfull0,
+                                         pair_id, num_pairs, total_work, (int)rank);
   }
 
   tc_fence_before();
@@ -626,8 +641,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+int encode_tmap(CUtensorMap* out, int dtype, int swizzle_bytes, const void* base, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -637,9 +652,11 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, dtype == PB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                  (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] stride0 %llu",
               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
@@ -649,6 +666,11 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
     return PB_ECUDA;
   }
   return PB_OK;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return encode_tmap(out, PB_BF16, 128, base, rank, dims, strides_bytes, box, elem_strides);
 }
 
 // Exact 128-row brick bw x bh x bn with bw | W, bh | H, bn | N; prefers wide bricks (long contiguous
@@ -668,13 +690,15 @@ static bool pick_brick(int W, int H, int N, int* bw, int* bh, int* bn) {
 
 static int num_sms();
 
-// Tile width: a multiple of 16 dividing n_cols, <= cap, minimising (waves over the SMs) x (per-tile cost);
-// the +64 charges the A-tile traffic every tile pays regardless of its width, so narrow tiles only win when
-// they remove a whole wave.
+// Tile width: a multiple of 32 (the epilogue's chunk) dividing n_cols, <= cap, minimising (waves over the SMs) x
+// (per-tile cost); the +64 charges the A-tile traffic every tile pays regardless of its width, so narrow
+// tiles only win when they remove a whole wave.  A width that is only a multiple of 16 is legal when it is
+// the whole output (its ragged last chunk is clipped at the tensor edge by the bulk store).
 static int pick_block_n(int n_cols, int cap, int m_tiles) {
+  if (n_cols <= cap && n_cols % 16 == 0 && n_cols % 32 != 0) return n_cols;
   int best = 0;
   long best_cost = 0;
-  for (int bn = cap - cap % 16; bn >= 64 || (best == 0 && bn >= 16); bn -= 16) {
+  for (int bn = cap - cap % 32; bn >= 64 || (best == 0 && bn >= 32); bn -= 32) {
     if (n_cols % bn != 0) continue;
     const long tiles = (long)m_tiles * (n_cols / bn);
     const long waves = (tiles + num_sms() - 1) / num_sms();
@@ -704,7 +728,8 @@ static int num_sms() {
 }
 
 template <int MODE, bool GEGLU, typename TC>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, size_t smem, cudaStream_t st) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                  const TcParams& p, size_t smem, cudaStream_t st) {
   static bool configured = false;
   auto kern = tc_gemm_kernel<MODE, GEGLU, TC>;
   if (!configured) {
@@ -714,13 +739,14 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams
   }
   int grid = p.m_tiles * p.n_tiles * p.splits;
   if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, p);
+  kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
   PB_LAUNCH_CHECK("tc_gemm_kernel");
   return PB_OK;
 }
 
 template <int MODE, bool GEGLU, typename TC>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, size_t smem, cudaStream_t st) {
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                       const TcParams& p, size_t smem, cudaStream_t st) {
   static bool configured = false;
   auto kern = tc_gemm_pair_kernel<MODE, GEGLU, TC>;
   if (!configured) {
@@ -730,20 +756,20 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP
   }
   int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
   if (pairs > num_sms() / 2) pairs = num_sms() / 2;
-  kern<<<2 * pairs, NUM_THREADS, smem, st>>>(tmA, tmB, p);   // __cluster_dims__(2,1,1)
+  kern<<<2 * pairs, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);   // __cluster_dims__(2,1,1)
   PB_LAUNCH_CHECK("tc_gemm_pair_kernel");
   return PB_OK;
 }
 
 template <int MODE, bool GEGLU>
-static int launch_c(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, size_t smem, cudaStream_t st,
-                    int c_dtype) {
+static int launch_c(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const CUtensorMap& r,
+                    const TcParams& p, size_t smem, cudaStream_t st, int c_dtype) {
   if (p.pair) {
-    if (c_dtype == PB_F32) return launch_pair<MODE, GEGLU, float>(a, b, p, smem, st);
-    return launch_pair<MODE, GEGLU, bf16>(a, b, p, smem, st);
+    if (c_dtype == PB_F32) return launch_pair<MODE, GEGLU, float>(a, b, c, r, p, smem, st);
+    return launch_pair<MODE, GEGLU, bf16>(a, b, c, r, p, smem, st);
   }
-  if (c_dtype == PB_F32) return launch<MODE, GEGLU, float>(a, b, p, smem, st);
-  return launch<MODE, GEGLU, bf16>(a, b, p, smem, st);
+  if (c_dtype == PB_F32) return launch<MODE, GEGLU, float>(a, b, c, r, p, smem, st);
+  return launch<MODE, GEGLU, bf16>(a, b, c, r, p, smem, st);
 }
 
 }  // namespace tc
@@ -761,26 +787,38 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   } while (0)
   if (a->a_dtype != PB_BF16) TC_UNSUPPORTED("pb_tc_gemm: operands must be bf16");
   const bool geglu = (a->epilogue & PB_EPI_GEGLU) != 0;
+  const bool has_res = (a->epilogue & PB_EPI_RESIDUAL) != 0;
   if (a->N % 16 != 0 || (geglu && a->N % 32 != 0)) TC_UNSUPPORTED("pb_tc_gemm: N=%lld not a multiple of 16", (long long)a->N);
   if (a->lda % 8 != 0) TC_UNSUPPORTED("pb_tc_gemm: lda must be a multiple of 8 (16-byte rows)");
   if ((reinterpret_cast<uintptr_t>(a->a) | reinterpret_cast<uintptr_t>(a->w)) & 15)
     TC_UNSUPPORTED("pb_tc_gemm: operands must be 16-byte aligned");
   if (geglu && (a->epilogue & (PB_EPI_ROWBIAS | PB_EPI_RESIDUAL)))
     TC_UNSUPPORTED("pb_tc_gemm: GEGLU cannot be combined with rowbias/residual");
+  // C and the residual move as bulk tensor copies: 16-byte aligned bases and row pitches
+  const uint64_t c_esz = a->c_dtype == PB_F32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(a->c) & 15) || (a->ldc * c_esz) % 16)
+    TC_UNSUPPORTED("pb_tc_gemm: C must be 16-byte aligned with a 16-byte row pitch");
+  if (has_res && ((reinterpret_cast<uintptr_t>(a->residual) & 15) || (a->ldr * 4) % 16))
+    TC_UNSUPPORTED("pb_tc_gemm: residual must be 16-byte aligned with a 16-byte row pitch");
+  if ((a->epilogue & PB_EPI_ROWBIAS) && ((reinterpret_cast<uintptr_t>(a->rowbias) & 15) || a->ld_rowbias % 4))
+    TC_UNSUPPORTED("pb_tc_gemm: rowbias must be 16-byte aligned");
 
   TcParams p;
   memset(&p, 0, sizeof(p));
-  p.c = a->c; p.bias = a->bias; p.rowbias = a->rowbias; p.residual = a->residual;
-  p.M = a->M; p.ldc = a->ldc; p.ldr = a->ldr; p.ldrb = a->ld_rowbias;
+  p.bias = a->bias; p.rowbias = a->rowbias;
+  p.M = a->M; p.ldrb = a->ld_rowbias;
   p.rb_rows = a->rowbias_rows > 0 ? a->rowbias_rows : 1;
   p.N = (int)a->N; p.epi = a->epilogue;
   p.geglu_half = geglu ? (int)(a->N / 2) : 0;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC, tmR;
   const int cin = a->a_mode == PB_A_LINEAR ? (int)a->K : a->cin;
   if (cin % BLOCK_K != 0) TC_UNSUPPORTED("pb_tc_gemm: K per tap (%d) must be a multiple of 64", cin);
   p.k_chunks = cin / BLOCK_K;
   const uint64_t esz = 2;
+  // geometry of the OUTPUT tensor as the C / residual maps see it: [cols][d1][d2][d3], box [32][b1][b2][b3]
+  uint64_t odims[3] = {0, 1, 1};
+  uint32_t obox[3] = {1, 1, 1};
   if (a->a_mode == PB_A_LINEAR) {
     p.taps = 1;
     p.m_tiles = (int)ceil_div(a->M, BLOCK_M);
@@ -788,6 +826,8 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     uint64_t str[1] = {(uint64_t)a->lda * esz};
     uint32_t box[2] = {BLOCK_K, BLOCK_M};
     rc = encode_tmap_bf16(&tmA, a->a, 2, dims, str, box, nullptr);
+    odims[0] = (uint64_t)a->M; obox[0] = BLOCK_M;
+    p.n_outer = 1;
   } else if (a->a_mode == PB_A_CONV3X3) {
     if (a->upsample) TC_UNSUPPORTED("pb_tc_gemm: upsample is folded only on the CUDA-core path (use pb_upsample2x_rows)");
     p.taps = 9;
@@ -807,6 +847,9 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     uint32_t box[4] = {BLOCK_K, (uint32_t)(s2 * p.bw), (uint32_t)(s2 * p.bh), (uint32_t)p.bn_img};
     uint32_t est[4] = {1, (uint32_t)s2, (uint32_t)s2, 1};
     rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box, s2 == 1 ? nullptr : est);
+    odims[0] = (uint64_t)W; odims[1] = (uint64_t)H; odims[2] = (uint64_t)n_img;
+    obox[0] = (uint32_t)p.bw; obox[1] = (uint32_t)p.bh; obox[2] = (uint32_t)p.bn_img;
+    p.n_outer = n_img;
   } else {
     p.taps = 3;
     const int HW = a->frame_rows, T = a->frames, nb = (int)(a->M / ((int64_t)HW * T));
@@ -819,6 +862,9 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     uint64_t str[3] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * HW, (uint64_t)a->lda * esz * HW * T};
     uint32_t box[4] = {BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, 1};
     rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box, nullptr);
+    odims[0] = (uint64_t)HW; odims[1] = (uint64_t)T; odims[2] = (uint64_t)nb;
+    obox[0] = (uint32_t)p.bw; obox[1] = (uint32_t)p.bh; obox[2] = 1;
+    p.n_outer = nb;
   }
   if (rc != PB_OK) return rc;
   const int n_cols = geglu ? (int)(a->N / 2) : (int)a->N;   // output columns
@@ -828,16 +874,19 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   p.n_tiles = n_cols / bn_out;
   // split-K (deterministic: fp32 partials in the caller's workspace + a fold kernel) when the grid is tiny
   const int k_iters = p.taps * p.k_chunks;
-  p.splits = 1; p.kps = k_iters; p.split_stride = 0;
+  p.splits = 1; p.kps = k_iters;
   const int want_splits = geglu ? 1 : pick_splits(p.m_tiles * p.n_tiles, k_iters);
-  if (want_splits > 1 && a->workspace &&
+  void* c_base = a->c;
+  int64_t ldc = a->ldc;
+  int c_dtype = a->c_dtype;
+  if (want_splits > 1 && a->workspace && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0 &&
       a->workspace_bytes >= (int64_t)want_splits * a->M * a->N * (int64_t)sizeof(float)) {
     p.kps = (k_iters + want_splits - 1) / want_splits;
     p.splits = (k_iters + p.kps - 1) / p.kps;
-    p.split_stride = a->M * a->N;
-    p.c = a->workspace; p.ldc = a->N; p.epi = 0;
-    p.bias = nullptr; p.rowbias = nullptr; p.residual = nullptr;
+    c_base = a->workspace; ldc = a->N; c_dtype = PB_F32; p.epi = 0;
+    p.bias = nullptr; p.rowbias = nullptr;
   }
+  const bool res_in_kernel = (p.epi & PB_EPI_RESIDUAL) != 0;
   // CTA pairs whenever there are enough 256-row tiles to occupy the 74 SM pairs and no split-K
   static const bool pair_enabled = []() { const char* e = getenv("PB_TC_PAIR"); return !(e && e[0] == '0'); }();
   p.pair = 0;
@@ -858,17 +907,42 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     rc = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box, nullptr);
     if (rc != PB_OK) return rc;
   }
+  {
+    // C: [cols][d1][d2][d3 * splits] (split-K partials are consecutive copies of the output in the workspace)
+    const uint64_t ce = c_dtype == PB_F32 ? 4 : 2;
+    uint64_t dims[4] = {(uint64_t)n_cols, odims[0], odims[1], odims[2] * (uint64_t)p.splits};
+    uint64_t str[3] = {(uint64_t)ldc * ce, (uint64_t)ldc * ce * odims[0], (uint64_t)ldc * ce * odims[0] * odims[1]};
+    uint32_t box[4] = {EPI_CHUNK, obox[0], obox[1], obox[2]};
+    if (a->a_mode == PB_A_LINEAR) {   // [cols][M][splits][1]
+      dims[2] = (uint64_t)p.splits; dims[3] = 1;
+      str[1] = (uint64_t)a->M * a->N * 4;      // only meaningful with split-K (fp32 workspace, ldc = N)
+      if (p.splits == 1) str[1] = str[0] * odims[0];
+      str[2] = str[1] * dims[2];
+    }
+    rc = encode_tmap(&tmC, c_dtype, c_dtype == PB_F32 ? 128 : 64, c_base, 4, dims, str, box, nullptr);
+    if (rc != PB_OK) return rc;
+    tmR = tmC;
+    if (res_in_kernel) {
+      uint64_t rdims[4] = {(uint64_t)n_cols, odims[0], odims[1], odims[2]};
+      uint64_t rstr[3] = {(uint64_t)a->ldr * 4, (uint64_t)a->ldr * 4 * odims[0], (uint64_t)a->ldr * 4 * odims[0] * odims[1]};
+      rc = encode_tmap(&tmR, PB_F32, 128, a->residual, 4, rdims, rstr, box, nullptr);
+      if (rc != PB_OK) return rc;
+    }
+  }
+  p.slot_bytes = (c_dtype == PB_F32 || res_in_kernel) ? EPI_SLOT_F32 : EPI_SLOT_BF16;
+  const int epi_bytes = 2 * EPI_SLOTS * p.slot_bytes;
   const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
-  p.stages = SMEM_PIPE_BUDGET / stage_bytes;
+  p.stages = (SMEM_TOTAL - 1024 - epi_bytes - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + 2 * EPI_STAGE_BYTES + BAR_BYTES;
+  if (p.stages < 2) TC_UNSUPPORTED("pb_tc_gemm: tile does not fit shared memory");
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + epi_bytes + BAR_BYTES;
 
   cudaStream_t st = to_stream(stream);
-  const int cd = p.splits > 1 ? PB_F32 : a->c_dtype;
   if (a->a_mode == PB_A_LINEAR)
-    rc = geglu ? launch_c<PB_A_LINEAR, true>(tmA, tmB, p, smem, st, cd) : launch_c<PB_A_LINEAR, false>(tmA, tmB, p, smem, st, cd);
-  else if (a->a_mode == PB_A_CONV3X3) rc = launch_c<PB_A_CONV3X3, false>(tmA, tmB, p, smem, st, cd);
-  else rc = launch_c<PB_A_CONVT3, false>(tmA, tmB, p, smem, st, cd);
+    rc = geglu ? launch_c<PB_A_LINEAR, true>(tmA, tmB, tmC, tmR, p, smem, st, c_dtype)
+               : launch_c<PB_A_LINEAR, false>(tmA, tmB, tmC, tmR, p, smem, st, c_dtype);
+  else if (a->a_mode == PB_A_CONV3X3) rc = launch_c<PB_A_CONV3X3, false>(tmA, tmB, tmC, tmR, p, smem, st, c_dtype);
+  else rc = launch_c<PB_A_CONVT3, false>(tmA, tmB, tmC, tmR, p, smem, st, c_dtype);
   if (rc != PB_OK || p.splits == 1) return rc;
   const int64_t total = a->M * (a->N / 4);
   int64_t blocks = ceil_div(total, 256);
@@ -900,7 +974,7 @@ extern "C" size_t pb_tc_gemm_workspace_bytes(const pb_gemm_args* a) {
   const int k_iters = taps * (cin / BLOCK_K);
   int worst = 1;
   for (int bn = 256; bn >= 16; bn -= 16) {
-    if (a->N % bn) continue;
+    if (a->N % bn || (bn % 32 && bn != a->N)) continue;
     const int s = pick_splits(m_tiles * (int)(a->N / bn), k_iters);
     if (s > worst) worst = s;
   }

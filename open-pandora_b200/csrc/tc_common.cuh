@@ -164,6 +164,9 @@ __device__ __forceinline__ bool elect_one() {
 // dims/box: rank entries, innermost first; strides_bytes: rank-1 entries (dims 1..rank-1).
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
+// general form: dtype PB_F32 / PB_BF16, swizzle 0 / 64 / 128 bytes (the box's inner extent must not exceed it)
+int encode_tmap(CUtensorMap* out, int dtype, int swizzle_bytes, const void* base, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 }  // namespace tc
 }  // namespace pb
