@@ -77,6 +77,13 @@ typedef struct pb_gemm_args {
      pb_tc_gemm_workspace_bytes(); NULL or too small => no split (results identical up to fp32 summation order) */
   void* workspace;
   int64_t workspace_bytes;
+  /* optional (pb_tc_gemm, fp32 output): per-column (sum, sumsq) of the stored values over every 32-row slab of
+     the output, colstats[(m / 32) * ld_colstats + 2 * n + {0, 1}] (ld_colstats in floats, >= 2 * N_out).  This is
+     the first pass of the GroupNorm that consumes the output (openaimodel3d.py:155,179,259-268; attention.py:265,331)
+     fused into the producer; pb_groupnorm_stats_cols folds it.  Written only when pb_tc_gemm_colstats_ok() says so
+     (tile rows must map to aligned 32-row slabs, no split-K); NULL = off. */
+  float* colstats;
+  int64_t ld_colstats;
 } pb_gemm_args;
 
 /* ---- library ---------------------------------------------------------------------------------- */
@@ -101,6 +108,8 @@ int pb_gemm(const pb_gemm_args* args, pb_stream_t stream);
  * (the caller then decides; there is no silent fallback inside the library).                      */
 int pb_tc_gemm(const pb_gemm_args* args, pb_stream_t stream);
 size_t pb_tc_gemm_workspace_bytes(const pb_gemm_args* args);
+/* 1 if pb_tc_gemm(args) will fill args->colstats, 0 if it will not (shape, split-K, dtype) */
+int pb_tc_gemm_colstats_ok(const pb_gemm_args* args);
 
 /* ---- GroupNorm(32) (+SiLU) ---------------------------------------------------------------------
  * Replaces nn.GroupNorm at basics.py:76-88, openaimodel3d.py:155,179,259-268,547 (eps 1e-5) and
@@ -116,6 +125,12 @@ int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_in
                        int64_t rows_per_inst, int64_t C, int32_t groups, float eps, const float* gamma,
                        const float* beta, float* scale_shift /* [n_inst, 2, C] */, void* ws,
                        size_t ws_bytes, pb_stream_t stream);
+/* Same result as pb_groupnorm_stats, but from the column statistics a producing pb_tc_gemm left behind
+ * (pb_gemm_args.colstats) instead of a pass over x: colstats rows are 32-row slabs, rows_per_inst % 32 == 0. */
+size_t pb_groupnorm_cols_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int32_t groups);
+int pb_groupnorm_stats_cols(const float* colstats, int64_t ld_colstats, int64_t n_inst, int64_t rows_per_inst,
+                            int64_t C, int32_t groups, float eps, const float* gamma, const float* beta,
+                            float* scale_shift /* [n_inst, 2, C] */, void* ws, size_t ws_bytes, pb_stream_t stream);
 int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype,
                        int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
                        const float* scale_shift, int32_t silu, pb_stream_t stream);

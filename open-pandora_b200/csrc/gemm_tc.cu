@@ -53,6 +53,8 @@ constexpr int SMEM_TOTAL = 227 * 1024;
 struct TcParams {
   const float* bias;
   const float* rowbias;
+  float* colstats;       // optional [ceil(M/32)][ld_cs] fp32: (sum, sumsq) per output column over each 32-row slab
+  int64_t ld_cs;
   int64_t M, ldrb, rb_rows;
   int N;                 // accumulator columns in total (weight rows)
   int block_n;           // accumulator columns per tile
@@ -271,6 +273,25 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
       // ---- (4) one bulk tensor store per chunk; prefetch the residual of this team's next chunk
       fence_proxy_async();
       team_bar_sync(team);
+      // ---- (4b) GroupNorm column statistics of the tile just staged (fp32 output only): warp w of the team
+      // owns the 32-row slab w, lane = column; rows of a swizzled slot are read conflict-free.  The bulk store
+      // reads the slot concurrently; the slot is not rewritten before this team's next barrier.
+      if (!OUT_BF16 && p.colstats != nullptr) {
+        const int w4 = (warp - 2) & 3;
+        const int64_t m0 = out_row<MODE>(p, m_tile, w4 * 32);
+        float cs_s = 0.f, cs_q = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          const int row = w4 * 32 + i;
+          float t;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t)
+                       : "r"(sbuf + (uint32_t)(row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2))));
+          cs_s += t;
+          cs_q = fmaf(t, t, cs_q);
+        }
+        if (lane < cw && m0 < p.M)
+          *reinterpret_cast<float2*>(p.colstats + (m0 >> 5) * p.ld_cs + 2 * (n0 + c0 + lane)) = make_float2(cs_s, cs_q);
+      }
       if (leader) {
         coords(work, ci, c, m_tile, n_tile);
         tma_store_4d(tmC, sbuf, c[0], c[1], c[2], c[3]);
@@ -775,16 +796,35 @@ static int launch_c(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMa
 }  // namespace tc
 }  // namespace pb
 
-extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
-  using namespace pb;
-  using namespace pb::tc;
-  int rc = validate_gemm_args(a, "pb_tc_gemm");
-  if (rc != PB_OK) return rc;
+namespace pb {
+namespace tc {
+
+// Everything pb_tc_gemm decides before it touches the device: tile geometry, split-K, CTA pairing, where C goes.
+struct TcPlan {
+  TcParams p;
+  int a_rank;
+  uint64_t adims[4], astr[3];
+  uint32_t abox[4], aest[4];
+  bool a_strided;
+  uint64_t odims[3];      // output tensor as the C / residual maps see it: [cols][d1][d2][d3]
+  uint32_t obox[3];
+  void* c_base;
+  int64_t ldc;
+  int c_dtype;
+  int n_cols;             // output columns
+  bool geglu;
+  bool colstats;          // the epilogue will write per-32-row column sums
+};
+
 #define TC_UNSUPPORTED(...)      \
   do {                           \
     set_error(__VA_ARGS__);      \
     return PB_EUNSUPPORTED;      \
   } while (0)
+
+static int tc_plan(const pb_gemm_args* a, TcPlan* pl) {
+  int rc = validate_gemm_args(a, "pb_tc_gemm");
+  if (rc != PB_OK) return rc;
   if (a->a_dtype != PB_BF16) TC_UNSUPPORTED("pb_tc_gemm: operands must be bf16");
   const bool geglu = (a->epilogue & PB_EPI_GEGLU) != 0;
   const bool has_res = (a->epilogue & PB_EPI_RESIDUAL) != 0;
@@ -803,31 +843,32 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   if ((a->epilogue & PB_EPI_ROWBIAS) && ((reinterpret_cast<uintptr_t>(a->rowbias) & 15) || a->ld_rowbias % 4))
     TC_UNSUPPORTED("pb_tc_gemm: rowbias must be 16-byte aligned");
 
-  TcParams p;
-  memset(&p, 0, sizeof(p));
+  memset(pl, 0, sizeof(*pl));
+  TcParams& p = pl->p;
   p.bias = a->bias; p.rowbias = a->rowbias;
   p.M = a->M; p.ldrb = a->ld_rowbias;
   p.rb_rows = a->rowbias_rows > 0 ? a->rowbias_rows : 1;
   p.N = (int)a->N; p.epi = a->epilogue;
   p.geglu_half = geglu ? (int)(a->N / 2) : 0;
+  pl->geglu = geglu;
 
-  CUtensorMap tmA, tmB, tmC, tmR;
   const int cin = a->a_mode == PB_A_LINEAR ? (int)a->K : a->cin;
   if (cin % BLOCK_K != 0) TC_UNSUPPORTED("pb_tc_gemm: K per tap (%d) must be a multiple of 64", cin);
   p.k_chunks = cin / BLOCK_K;
   const uint64_t esz = 2;
-  // geometry of the OUTPUT tensor as the C / residual maps see it: [cols][d1][d2][d3], box [32][b1][b2][b3]
-  uint64_t odims[3] = {0, 1, 1};
-  uint32_t obox[3] = {1, 1, 1};
+  pl->odims[0] = 0; pl->odims[1] = 1; pl->odims[2] = 1;
+  pl->obox[0] = 1; pl->obox[1] = 1; pl->obox[2] = 1;
+  bool slab_ok;   // every 32-row slab of a tile is 32 consecutive output rows starting at a multiple of 32
   if (a->a_mode == PB_A_LINEAR) {
     p.taps = 1;
     p.m_tiles = (int)ceil_div(a->M, BLOCK_M);
-    uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
-    uint64_t str[1] = {(uint64_t)a->lda * esz};
-    uint32_t box[2] = {BLOCK_K, BLOCK_M};
-    rc = encode_tmap_bf16(&tmA, a->a, 2, dims, str, box, nullptr);
-    odims[0] = (uint64_t)a->M; obox[0] = BLOCK_M;
+    pl->a_rank = 2;
+    pl->adims[0] = (uint64_t)a->K; pl->adims[1] = (uint64_t)a->M;
+    pl->astr[0] = (uint64_t)a->lda * esz;
+    pl->abox[0] = BLOCK_K; pl->abox[1] = BLOCK_M;
+    pl->odims[0] = (uint64_t)a->M; pl->obox[0] = BLOCK_M;
     p.n_outer = 1;
+    slab_ok = true;
   } else if (a->a_mode == PB_A_CONV3X3) {
     if (a->upsample) TC_UNSUPPORTED("pb_tc_gemm: upsample is folded only on the CUDA-core path (use pb_upsample2x_rows)");
     p.taps = 9;
@@ -841,15 +882,16 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     if (s2 * p.bw > 256 || s2 * p.bh > 256) TC_UNSUPPORTED("pb_tc_gemm: strided box exceeds the TMA box limit");
     p.tiles_x = W / p.bw; p.tiles_y = H / p.bh;
     p.m_tiles = p.tiles_x * p.tiles_y * (n_img / p.bn_img);
-    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)a->in_w, (uint64_t)a->in_h, (uint64_t)n_img};
-    uint64_t str[3] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * a->in_w,
-                       (uint64_t)a->lda * esz * a->in_w * a->in_h};
-    uint32_t box[4] = {BLOCK_K, (uint32_t)(s2 * p.bw), (uint32_t)(s2 * p.bh), (uint32_t)p.bn_img};
-    uint32_t est[4] = {1, (uint32_t)s2, (uint32_t)s2, 1};
-    rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box, s2 == 1 ? nullptr : est);
-    odims[0] = (uint64_t)W; odims[1] = (uint64_t)H; odims[2] = (uint64_t)n_img;
-    obox[0] = (uint32_t)p.bw; obox[1] = (uint32_t)p.bh; obox[2] = (uint32_t)p.bn_img;
+    pl->a_rank = 4;
+    pl->adims[0] = (uint64_t)cin; pl->adims[1] = (uint64_t)a->in_w; pl->adims[2] = (uint64_t)a->in_h; pl->adims[3] = (uint64_t)n_img;
+    pl->astr[0] = (uint64_t)a->lda * esz; pl->astr[1] = pl->astr[0] * a->in_w; pl->astr[2] = pl->astr[1] * a->in_h;
+    pl->abox[0] = BLOCK_K; pl->abox[1] = (uint32_t)(s2 * p.bw); pl->abox[2] = (uint32_t)(s2 * p.bh); pl->abox[3] = (uint32_t)p.bn_img;
+    pl->aest[0] = 1; pl->aest[1] = (uint32_t)s2; pl->aest[2] = (uint32_t)s2; pl->aest[3] = 1;
+    pl->a_strided = s2 != 1;
+    pl->odims[0] = (uint64_t)W; pl->odims[1] = (uint64_t)H; pl->odims[2] = (uint64_t)n_img;
+    pl->obox[0] = (uint32_t)p.bw; pl->obox[1] = (uint32_t)p.bh; pl->obox[2] = (uint32_t)p.bn_img;
     p.n_outer = n_img;
+    slab_ok = ((int64_t)W * H) % 32 == 0 && ((p.bw % 32 == 0) || (p.bw == W && 32 % p.bw == 0 && p.bh % (32 / p.bw) == 0));
   } else {
     p.taps = 3;
     const int HW = a->frame_rows, T = a->frames, nb = (int)(a->M / ((int64_t)HW * T));
@@ -858,16 +900,17 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     if (!pick_brick(HW, T, 1, &p.bw, &p.bh, &one)) TC_UNSUPPORTED("pb_tc_gemm: %d pixels x %d frames has no exact 128-row brick", HW, T);
     p.tiles_x = HW / p.bw; p.tiles_y = T / p.bh;
     p.m_tiles = p.tiles_x * p.tiles_y * nb;
-    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)HW, (uint64_t)T, (uint64_t)nb};
-    uint64_t str[3] = {(uint64_t)a->lda * esz, (uint64_t)a->lda * esz * HW, (uint64_t)a->lda * esz * HW * T};
-    uint32_t box[4] = {BLOCK_K, (uint32_t)p.bw, (uint32_t)p.bh, 1};
-    rc = encode_tmap_bf16(&tmA, a->a, 4, dims, str, box, nullptr);
-    odims[0] = (uint64_t)HW; odims[1] = (uint64_t)T; odims[2] = (uint64_t)nb;
-    obox[0] = (uint32_t)p.bw; obox[1] = (uint32_t)p.bh; obox[2] = 1;
+    pl->a_rank = 4;
+    pl->adims[0] = (uint64_t)cin; pl->adims[1] = (uint64_t)HW; pl->adims[2] = (uint64_t)T; pl->adims[3] = (uint64_t)nb;
+    pl->astr[0] = (uint64_t)a->lda * esz; pl->astr[1] = pl->astr[0] * HW; pl->astr[2] = pl->astr[1] * T;
+    pl->abox[0] = BLOCK_K; pl->abox[1] = (uint32_t)p.bw; pl->abox[2] = (uint32_t)p.bh; pl->abox[3] = 1;
+    pl->odims[0] = (uint64_t)HW; pl->odims[1] = (uint64_t)T; pl->odims[2] = (uint64_t)nb;
+    pl->obox[0] = (uint32_t)p.bw; pl->obox[1] = (uint32_t)p.bh; pl->obox[2] = 1;
     p.n_outer = nb;
+    slab_ok = ((int64_t)HW * T) % 32 == 0 && ((p.bw % 32 == 0) || (p.bw == HW && 32 % p.bw == 0 && p.bh % (32 / p.bw) == 0));
   }
-  if (rc != PB_OK) return rc;
   const int n_cols = geglu ? (int)(a->N / 2) : (int)a->N;   // output columns
+  pl->n_cols = n_cols;
   const int bn_out = pick_block_n(n_cols, geglu ? 128 : 256, p.m_tiles);
   if (bn_out == 0) TC_UNSUPPORTED("pb_tc_gemm: no tile width divides N=%d", n_cols);
   p.block_n = geglu ? 2 * bn_out : bn_out;
@@ -876,17 +919,14 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   const int k_iters = p.taps * p.k_chunks;
   p.splits = 1; p.kps = k_iters;
   const int want_splits = geglu ? 1 : pick_splits(p.m_tiles * p.n_tiles, k_iters);
-  void* c_base = a->c;
-  int64_t ldc = a->ldc;
-  int c_dtype = a->c_dtype;
+  pl->c_base = a->c; pl->ldc = a->ldc; pl->c_dtype = a->c_dtype;
   if (want_splits > 1 && a->workspace && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0 &&
       a->workspace_bytes >= (int64_t)want_splits * a->M * a->N * (int64_t)sizeof(float)) {
     p.kps = (k_iters + want_splits - 1) / want_splits;
     p.splits = (k_iters + p.kps - 1) / p.kps;
-    c_base = a->workspace; ldc = a->N; c_dtype = PB_F32; p.epi = 0;
+    pl->c_base = a->workspace; pl->ldc = a->N; pl->c_dtype = PB_F32; p.epi = 0;
     p.bias = nullptr; p.rowbias = nullptr;
   }
-  const bool res_in_kernel = (p.epi & PB_EPI_RESIDUAL) != 0;
   // CTA pairs whenever there are enough 256-row tiles to occupy the 74 SM pairs and no split-K
   static const bool pair_enabled = []() { const char* e = getenv("PB_TC_PAIR"); return !(e && e[0] == '0'); }();
   p.pair = 0;
@@ -899,6 +939,37 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
       p.n_tiles = n_cols / bn_pair;
     }
   }
+  // fused GroupNorm column statistics: fp32 output written by this kernel itself, slabs aligned in row space
+  pl->colstats = a->colstats != nullptr && a->c_dtype == PB_F32 && p.splits == 1 && !geglu && slab_ok &&
+                 a->ld_colstats >= 2 * (int64_t)n_cols && a->ld_colstats % 2 == 0 &&
+                 (reinterpret_cast<uintptr_t>(a->colstats) & 7) == 0;
+  if (pl->colstats) { p.colstats = a->colstats; p.ld_cs = a->ld_colstats; }
+  const bool res_in_kernel = (p.epi & PB_EPI_RESIDUAL) != 0;
+  p.slot_bytes = (pl->c_dtype == PB_F32 || res_in_kernel) ? EPI_SLOT_F32 : EPI_SLOT_BF16;
+  return PB_OK;
+}
+
+}  // namespace tc
+}  // namespace pb
+
+extern "C" int pb_tc_gemm_colstats_ok(const pb_gemm_args* a) {
+  pb::tc::TcPlan pl;
+  if (pb::tc::tc_plan(a, &pl) != PB_OK) return 0;
+  return pl.colstats ? 1 : 0;
+}
+
+extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
+  using namespace pb;
+  using namespace pb::tc;
+  TcPlan pl;
+  int rc = tc_plan(a, &pl);
+  if (rc != PB_OK) return rc;
+  TcParams& p = pl.p;
+  const bool geglu = pl.geglu;
+  const uint64_t esz = 2;
+  CUtensorMap tmA, tmB, tmC, tmR;
+  rc = encode_tmap_bf16(&tmA, a->a, pl.a_rank, pl.adims, pl.astr, pl.abox, pl.a_strided ? pl.aest : nullptr);
+  if (rc != PB_OK) return rc;
   {
     uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->N};
     uint64_t str[1] = {(uint64_t)a->K * esz};
@@ -907,29 +978,29 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
     rc = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box, nullptr);
     if (rc != PB_OK) return rc;
   }
+  const bool res_in_kernel = (p.epi & PB_EPI_RESIDUAL) != 0;
   {
     // C: [cols][d1][d2][d3 * splits] (split-K partials are consecutive copies of the output in the workspace)
-    const uint64_t ce = c_dtype == PB_F32 ? 4 : 2;
-    uint64_t dims[4] = {(uint64_t)n_cols, odims[0], odims[1], odims[2] * (uint64_t)p.splits};
-    uint64_t str[3] = {(uint64_t)ldc * ce, (uint64_t)ldc * ce * odims[0], (uint64_t)ldc * ce * odims[0] * odims[1]};
-    uint32_t box[4] = {EPI_CHUNK, obox[0], obox[1], obox[2]};
+    const uint64_t* od = pl.odims;
+    const uint64_t ce = pl.c_dtype == PB_F32 ? 4 : 2;
+    uint64_t dims[4] = {(uint64_t)pl.n_cols, od[0], od[1], od[2] * (uint64_t)p.splits};
+    uint64_t str[3] = {(uint64_t)pl.ldc * ce, (uint64_t)pl.ldc * ce * od[0], (uint64_t)pl.ldc * ce * od[0] * od[1]};
+    uint32_t box[4] = {EPI_CHUNK, pl.obox[0], pl.obox[1], pl.obox[2]};
     if (a->a_mode == PB_A_LINEAR) {   // [cols][M][splits][1]
       dims[2] = (uint64_t)p.splits; dims[3] = 1;
-      str[1] = (uint64_t)a->M * a->N * 4;      // only meaningful with split-K (fp32 workspace, ldc = N)
-      if (p.splits == 1) str[1] = str[0] * odims[0];
+      str[1] = p.splits > 1 ? (uint64_t)a->M * a->N * 4 : str[0] * od[0];   // split pitch (fp32 workspace, ldc = N)
       str[2] = str[1] * dims[2];
     }
-    rc = encode_tmap(&tmC, c_dtype, c_dtype == PB_F32 ? 128 : 64, c_base, 4, dims, str, box, nullptr);
+    rc = encode_tmap(&tmC, pl.c_dtype, pl.c_dtype == PB_F32 ? 128 : 64, pl.c_base, 4, dims, str, box, nullptr);
     if (rc != PB_OK) return rc;
     tmR = tmC;
     if (res_in_kernel) {
-      uint64_t rdims[4] = {(uint64_t)n_cols, odims[0], odims[1], odims[2]};
-      uint64_t rstr[3] = {(uint64_t)a->ldr * 4, (uint64_t)a->ldr * 4 * odims[0], (uint64_t)a->ldr * 4 * odims[0] * odims[1]};
+      uint64_t rdims[4] = {(uint64_t)pl.n_cols, od[0], od[1], od[2]};
+      uint64_t rstr[3] = {(uint64_t)a->ldr * 4, (uint64_t)a->ldr * 4 * od[0], (uint64_t)a->ldr * 4 * od[0] * od[1]};
       rc = encode_tmap(&tmR, PB_F32, 128, a->residual, 4, rdims, rstr, box, nullptr);
       if (rc != PB_OK) return rc;
     }
   }
-  p.slot_bytes = (c_dtype == PB_F32 || res_in_kernel) ? EPI_SLOT_F32 : EPI_SLOT_BF16;
   const int epi_bytes = 2 * EPI_SLOTS * p.slot_bytes;
   const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = (SMEM_TOTAL - 1024 - epi_bytes - BAR_BYTES) / stage_bytes;
@@ -938,6 +1009,7 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + epi_bytes + BAR_BYTES;
 
   cudaStream_t st = to_stream(stream);
+  const int c_dtype = pl.c_dtype;
   if (a->a_mode == PB_A_LINEAR)
     rc = geglu ? launch_c<PB_A_LINEAR, true>(tmA, tmB, tmC, tmR, p, smem, st, c_dtype)
                : launch_c<PB_A_LINEAR, false>(tmA, tmB, tmC, tmR, p, smem, st, c_dtype);
@@ -960,8 +1032,8 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
                                                                  a->ldc, bias, rowb, a->ld_rowbias, rbr, resid, a->ldr);
   PB_LAUNCH_CHECK("splitk_reduce_kernel");
   return PB_OK;
-#undef TC_UNSUPPORTED
 }
+#undef TC_UNSUPPORTED
 
 extern "C" size_t pb_tc_gemm_workspace_bytes(const pb_gemm_args* a) {
   // upper bound for the split-K partials of this problem (0 when split-K will not be used)

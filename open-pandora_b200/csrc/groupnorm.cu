@@ -36,6 +36,14 @@ static inline int gn_splits(int64_t n_inst, int64_t R) {
 
 constexpr int GN_MAX_C = 2560;
 
+// slab-range splits of the column-statistics fold: aim at ~4 CTAs per SM, at least 16 slabs per CTA
+static inline int gn_cols_splits(int64_t n_inst, int64_t R, int groups) {
+  const int64_t ctas = n_inst * groups, slabs = R >> 5;
+  int64_t s = ceil_div(148 * 4, ctas);
+  if (s > slabs / 16) s = slabs / 16;
+  return s < 1 ? 1 : (int)s;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_partial_kernel(const T* __restrict__ x, int64_t ldx, int64_t R, int C, int G, int splits, int TX, int TY,
@@ -126,6 +134,118 @@ gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64
   if (threadIdx.x == 0) {
     const double ss = red[0][0] + red[0][1] + red[0][2] + red[0][3];
     const double qq = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    const double cnt = (double)R * cpg;
+    const double mean = ss / cnt;
+    double var = qq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[0] = (float)mean;
+    stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float meanf = stat[0], rstd = stat[1];
+  float* sc = scale_shift + (int64_t)inst * 2 * C;
+  for (int i = threadIdx.x; i < cpg; i += 128) {
+    const int c = g * cpg + i;
+    const float a = rstd * gamma[c];
+    sc[c] = a;
+    sc[C + c] = beta[c] - meanf * a;
+  }
+}
+
+// Fold of the column statistics written by the producing GEMM's epilogue (pb_gemm_args.colstats): one CTA per
+// (instance, group) sums (R/32 slabs) x (C/G columns) float2 entries in fp64, then emits the per-channel affine.
+__global__ void __launch_bounds__(256)
+gn_finalize_cols_kernel(const float* __restrict__ cs, int64_t ld_cs, int C, int G, int64_t R, float eps,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        float* __restrict__ scale_shift /* [n_inst, 2, C] */) {
+  __shared__ double red[2][8];
+  __shared__ float stat[2];
+  const int inst = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  const int64_t slabs = R >> 5;
+  const float* base = cs + (int64_t)inst * slabs * ld_cs + 2 * (int64_t)g * cpg;
+  const int64_t total = slabs * cpg;
+  double s = 0.0, q = 0.0;
+  for (int64_t i = threadIdx.x; i < total; i += 256) {
+    const int64_t sl = i / cpg;
+    const int c = (int)(i - sl * cpg);
+    const float2 v = *reinterpret_cast<const float2*>(base + sl * ld_cs + 2 * c);
+    s += (double)v.x; q += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = s; red[1][w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ss = 0.0, qq = 0.0;
+    for (int i = 0; i < 8; ++i) { ss += red[0][i]; qq += red[1][i]; }
+    const double cnt = (double)R * cpg;
+    const double mean = ss / cnt;
+    double var = qq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[0] = (float)mean;
+    stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float meanf = stat[0], rstd = stat[1];
+  float* sc = scale_shift + (int64_t)inst * 2 * C;
+  for (int i = threadIdx.x; i < cpg; i += 256) {
+    const int c = g * cpg + i;
+    const float a = rstd * gamma[c];
+    sc[c] = a;
+    sc[C + c] = beta[c] - meanf * a;
+  }
+}
+
+// Few (instance, group) pairs but many slabs (clip-wide norms: 2 x 32 CTAs would each walk thousands of slabs):
+// grid (n_inst * G, splits) partial fp64 sums -> ws[(inst*G + g) * splits + sp]; gn_finalize_f64_kernel folds them.
+__global__ void __launch_bounds__(256)
+gn_cols_partial_kernel(const float* __restrict__ cs, int64_t ld_cs, int C, int G, int64_t R, int splits,
+                       double* __restrict__ ws) {
+  __shared__ double red[2][8];
+  const int inst = blockIdx.x / G, g = blockIdx.x % G, sp = blockIdx.y;
+  const int cpg = C / G;
+  const int64_t slabs = R >> 5;
+  const int64_t s0 = slabs * sp / splits, s1 = slabs * (sp + 1) / splits;
+  const float* base = cs + ((int64_t)inst * slabs + s0) * ld_cs + 2 * (int64_t)g * cpg;
+  const int64_t total = (s1 - s0) * cpg;
+  double s = 0.0, q = 0.0;
+  for (int64_t i = threadIdx.x; i < total; i += 256) {
+    const int64_t sl = i / cpg;
+    const int c = (int)(i - sl * cpg);
+    const float2 v = *reinterpret_cast<const float2*>(base + sl * ld_cs + 2 * c);
+    s += (double)v.x; q += (double)v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = s; red[1][w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ss = 0.0, qq = 0.0;
+    for (int i = 0; i < 8; ++i) { ss += red[0][i]; qq += red[1][i]; }
+    ws[((int64_t)blockIdx.x * splits + sp) * 2] = ss;
+    ws[((int64_t)blockIdx.x * splits + sp) * 2 + 1] = qq;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+gn_finalize_f64_kernel(const double* __restrict__ ws, int splits, int C, int G, int64_t R, float eps,
+                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float* __restrict__ scale_shift) {
+  __shared__ float stat[2];
+  const int inst = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  if (threadIdx.x == 0) {
+    double ss = 0.0, qq = 0.0;
+    for (int i = 0; i < splits; ++i) { ss += ws[((int64_t)blockIdx.x * splits + i) * 2]; qq += ws[((int64_t)blockIdx.x * splits + i) * 2 + 1]; }
     const double cnt = (double)R * cpg;
     const double mean = ss / cnt;
     double var = qq / cnt - mean * mean;
@@ -265,6 +385,40 @@ int pb_groupnorm_stats(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_in
   gn_finalize_kernel<<<(unsigned)(n_inst * groups), 128, 0, st>>>(
       reinterpret_cast<const float*>(ws), splits, (int)C, groups, rows_per_inst, eps, gamma, beta, scale_shift);
   PB_LAUNCH_CHECK("gn_finalize_kernel");
+  return PB_OK;
+}
+
+size_t pb_groupnorm_cols_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int32_t groups) {
+  if (n_inst <= 0 || rows_per_inst <= 0 || groups <= 0) return 0;
+  const int s = pb::gn_cols_splits(n_inst, rows_per_inst, groups);
+  return s > 1 ? (size_t)n_inst * groups * s * 2 * sizeof(double) : 0;
+}
+
+int pb_groupnorm_stats_cols(const float* colstats, int64_t ld_colstats, int64_t n_inst, int64_t rows_per_inst,
+                            int64_t C, int32_t groups, float eps, const float* gamma, const float* beta,
+                            float* scale_shift, void* ws, size_t ws_bytes, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(colstats && scale_shift && gamma && beta, "pb_groupnorm_stats_cols: null pointer");
+  PB_REQUIRE(n_inst > 0 && rows_per_inst > 0 && C > 0 && groups > 0 && C % groups == 0,
+             "pb_groupnorm_stats_cols: bad sizes");
+  PB_REQUIRE(rows_per_inst % 32 == 0, "pb_groupnorm_stats_cols: rows_per_inst must be a multiple of 32 (the slab)");
+  PB_REQUIRE(ld_colstats >= 2 * C && ld_colstats % 2 == 0, "pb_groupnorm_stats_cols: bad ld_colstats");
+  const int splits = gn_cols_splits(n_inst, rows_per_inst, groups);
+  if (splits > 1) {
+    PB_REQUIRE(ws && ws_bytes >= pb_groupnorm_cols_ws_bytes(n_inst, rows_per_inst, groups),
+               "pb_groupnorm_stats_cols: workspace too small");
+    dim3 grid((unsigned)(n_inst * groups), (unsigned)splits);
+    gn_cols_partial_kernel<<<grid, 256, 0, to_stream(stream)>>>(colstats, ld_colstats, (int)C, groups, rows_per_inst,
+                                                                splits, reinterpret_cast<double*>(ws));
+    PB_LAUNCH_CHECK("gn_cols_partial_kernel");
+    gn_finalize_f64_kernel<<<(unsigned)(n_inst * groups), 128, 0, to_stream(stream)>>>(
+        reinterpret_cast<const double*>(ws), splits, (int)C, groups, rows_per_inst, eps, gamma, beta, scale_shift);
+    PB_LAUNCH_CHECK("gn_finalize_f64_kernel");
+    return PB_OK;
+  }
+  gn_finalize_cols_kernel<<<(unsigned)(n_inst * groups), 256, 0, to_stream(stream)>>>(
+      colstats, ld_colstats, (int)C, groups, rows_per_inst, eps, gamma, beta, scale_shift);
+  PB_LAUNCH_CHECK("gn_finalize_cols_kernel");
   return PB_OK;
 }
 

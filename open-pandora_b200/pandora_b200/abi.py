@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("out_w", C.c_int32), ("stride", C.c_int32), ("upsample", C.c_int32),
         ("frames", C.c_int32), ("frame_rows", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
+        ("colstats", C.c_void_p), ("ld_colstats", C.c_int64),
     ]
 
 
@@ -59,6 +60,9 @@ SYMBOLS = {
     "pb_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "pb_tc_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "pb_tc_gemm_workspace_bytes": (_sz, [C.POINTER(GemmArgs)]),
+    "pb_tc_gemm_colstats_ok": (C.c_int, [C.POINTER(GemmArgs)]),
+    "pb_groupnorm_cols_ws_bytes": (_sz, [_i64, _i64, _i32]),
+    "pb_groupnorm_stats_cols": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pb_groupnorm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "pb_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pb_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _i32, _vp]),
@@ -183,8 +187,11 @@ def supports_tc():
 
 
 def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=False,
-         mode=A_LINEAR, conv=None, convt=None, tc=False, M=None, K=None):
-    """c = epilogue(gather(a) @ w.T).  a, c, residual are 2-D row views; w is [N, K] contiguous."""
+         mode=A_LINEAR, conv=None, convt=None, tc=False, M=None, K=None, colstats=None):
+    """c = epilogue(gather(a) @ w.T).  a, c, residual are 2-D row views; w is [N, K] contiguous.
+    colstats: optional fp32 row view [ceil(M/32), >= 2*N_out] that the tcgen05 epilogue fills with per-slab
+    column (sum, sumsq) for the GroupNorm that follows.  Returns 0 (shape not supported by the tcgen05 path),
+    1 (launched) or 2 (launched and colstats written)."""
     global launches
     g = GemmArgs()
     g.a, g.lda = _rows(a)
@@ -216,6 +223,10 @@ def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=
     lib = load()
     fn = lib.pb_tc_gemm if tc else lib.pb_gemm
     ws = None
+    wrote_stats = False
+    if tc and colstats is not None:
+        assert colstats.dtype == torch.float32 and colstats.shape[0] * 32 >= g.M
+        g.colstats, g.ld_colstats = _rows(colstats)
     if tc and g.M <= 9472:                     # split-K scratch only matters for launches with < 74 row tiles
         nb = lib.pb_tc_gemm_workspace_bytes(C.byref(g))
         if nb:
@@ -225,34 +236,49 @@ def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=
                 2 * g.M * g.N * g.K, (g.M * g.K // (1, 9, 3)[mode] + g.N * g.K) * a.element_size() + _nbytes(c, residual),
                 lambda: f"M{g.M} N{g.N} K{g.K} epi{epi} out{'f32' if g.c_dtype == F32 else 'bf16'}"
                         + (f" s{g.stride}" if mode == A_CONV3X3 and g.stride != 1 else ""))
+    if tc and colstats is not None:
+        wrote_stats = lib.pb_tc_gemm_colstats_ok(C.byref(g)) == 1
     rc = fn(C.byref(g), _stream())
     if rc == E_UNSUPPORTED and tc:
-        return False
+        return 0
     _check(rc, "pb_tc_gemm" if tc else "pb_gemm")
     _tock(tok)
     launches += 1
-    return True
+    return 2 if wrote_stats else 1
 
 
-def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32):
-    """y = GroupNorm(x) [* SiLU]; x, y 2-D row views [n_inst*rows_per_inst, C]."""
+def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32, colstats=None):
+    """y = GroupNorm(x) [* SiLU]; x, y 2-D row views [n_inst*rows_per_inst, C].  colstats: the column statistics
+    the producer of x left behind (see `gemm`), which replace the statistics pass over x."""
     global launches
     lib = load()
     Cc = x.shape[1]
-    ws_bytes = lib.pb_groupnorm_ws_bytes(n_inst, rows_per_inst, Cc)
-    ws = torch.empty(ws_bytes // 4 + n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
-    stats = ws[ws_bytes // 4:]
     xp, ldx = _rows(x)
     yp, ldy = _rows(y)
     st = _stream()
-    tok = _tick("groupnorm", 0, 2 * _nbytes(x) + _nbytes(y), f"inst{n_inst} rows{rows_per_inst} C{Cc}")
-    _check(lib.pb_groupnorm_stats(xp, dt(x), ldx, n_inst, rows_per_inst, Cc, groups, eps, gamma.data_ptr(),
-                                  beta.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes, st),
-           "pb_groupnorm_stats")
+    if colstats is not None:
+        assert rows_per_inst % 32 == 0 and colstats.shape[0] * 32 == x.shape[0] and colstats.shape[1] == 2 * Cc
+        stats = torch.empty(n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
+        cp, ldcs = _rows(colstats)
+        tok = _tick("groupnorm_fused", 0, _nbytes(x) + _nbytes(y), f"inst{n_inst} rows{rows_per_inst} C{Cc}")
+        wsb = lib.pb_groupnorm_cols_ws_bytes(n_inst, rows_per_inst, groups)
+        ws = torch.empty(wsb // 8, dtype=torch.float64, device=x.device) if wsb else None
+        _check(lib.pb_groupnorm_stats_cols(cp, ldcs, n_inst, rows_per_inst, Cc, groups, eps, gamma.data_ptr(),
+                                           beta.data_ptr(), stats.data_ptr(), _ptr(ws), wsb, st),
+               "pb_groupnorm_stats_cols")
+        launches += 3 if wsb else 2
+    else:
+        ws_bytes = lib.pb_groupnorm_ws_bytes(n_inst, rows_per_inst, Cc)
+        ws = torch.empty(ws_bytes // 4 + n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
+        stats = ws[ws_bytes // 4:]
+        tok = _tick("groupnorm", 0, 2 * _nbytes(x) + _nbytes(y), f"inst{n_inst} rows{rows_per_inst} C{Cc}")
+        _check(lib.pb_groupnorm_stats(xp, dt(x), ldx, n_inst, rows_per_inst, Cc, groups, eps, gamma.data_ptr(),
+                                      beta.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes, st),
+               "pb_groupnorm_stats")
+        launches += 3
     _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc,
                                   stats.data_ptr(), int(silu), st), "pb_groupnorm_apply")
     _tock(tok)
-    launches += 3
     return stats
 
 

@@ -335,6 +335,23 @@ class _Runner:
     def new(self, rows, cols, dtype):
         return torch.empty((rows, cols), dtype=dtype, device=self.dev)
 
+    def new_trunk(self, rows, cols):
+        """fp32 rows that a GroupNorm may read next.  On the tcgen05 path they carry a column-statistics buffer
+        (`_cs`, [rows/32, 2*cols]) that the producing GEMM's epilogue fills, so the norm needs no pass over the
+        tensor for its statistics (pb_gemm_args.colstats)."""
+        t = self.new(rows, cols, torch.float32)
+        t._cs = self.new(rows // 32, 2 * cols, torch.float32) if (self.use_tc and rows % 32 == 0) else None
+        t._cs_valid, t._cs_parts = False, [t]
+        return t
+
+    def trunk_cols(self, t, c0, c1):
+        """Column slice [c0, c1) of a trunk tensor, sharing its storage and its statistics buffer: producers write
+        their half of a skip concatenation (openaimodel3d.py:600) in place instead of copying it there."""
+        v = t[:, c0:c1]
+        v._cs = None if t._cs is None else t._cs[:, 2 * c0:2 * c1]
+        v._cs_valid, v._cs_parts = False, [v]
+        return v
+
     # ---- packed weights -----------------------------------------------------------------------
     def _param(self, name):
         if self.sd is None:
@@ -377,12 +394,22 @@ class _Runner:
         return self.w(("conv", name, dtype), build)
 
     # ---- kernel wrappers ----------------------------------------------------------------------
-    def gemm(self, a, w, out_cols, out_dtype, tc_ok=True, out=None, **kw):
+    def gemm(self, a, w, out_cols, out_dtype, tc_ok=True, out=None, stats=False, **kw):
+        """stats: the result feeds a GroupNorm -> allocate it as a trunk tensor and let the epilogue leave the
+        norm's column statistics behind."""
         M = kw.pop("M", a.shape[0])
-        c = self.new(M, out_cols, out_dtype) if out is None else out
-        done = False
+        if out is not None:
+            c = out
+        elif stats and out_dtype == torch.float32:
+            c = self.new_trunk(M, out_cols)
+        else:
+            c = self.new(M, out_cols, out_dtype)
+        done = 0
         if self.use_tc and tc_ok and a.dtype == torch.bfloat16:
-            done = abi.gemm(a, w, c, tc=True, M=M, **kw)
+            cs = getattr(c, "_cs", None) if stats else None
+            done = abi.gemm(a, w, c, tc=True, M=M, colstats=cs, **kw)
+            if done == 2:
+                c._cs_valid = True
         if not done:
             if kw.get("geglu"):
                 kw = dict(kw, geglu=False)
@@ -393,13 +420,13 @@ class _Runner:
                 abi.gemm(a, w, c, M=M, **kw)
         return c
 
-    def linear(self, a, wname, bname, out_dtype, residual=None, geglu=False, w=None, out=None):
+    def linear(self, a, wname, bname, out_dtype, residual=None, geglu=False, w=None, out=None, stats=False):
         w = self.lin_w(wname) if w is None else w
         if a.dtype != w.dtype:
             a = self.cast(a, w.dtype)
         bias = None if bname is None else (self.vec(bname) if isinstance(bname, str) else bname)
         n_out = w.shape[0] // 2 if geglu else w.shape[0]
-        return self.gemm(a, w, n_out, out_dtype, bias=bias, residual=residual, geglu=geglu, out=out)
+        return self.gemm(a, w, n_out, out_dtype, bias=bias, residual=residual, geglu=geglu, out=out, stats=stats)
 
     def cast(self, a, dtype):
         if a.dtype == dtype:
@@ -417,7 +444,12 @@ class _Runner:
             abi.groupnorm_sp(x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu,
                              self.sp.all_reduce_sum, rows * self.sp.P)
         else:
-            abi.groupnorm(x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu)
+            # statistics left behind by the producer(s) of x (both halves for a skip concatenation)
+            cs, parts = getattr(x, "_cs", None), getattr(x, "_cs_parts", None)
+            if cs is None or not parts or rows % 32 or not all(getattr(q, "_cs_valid", False) for q in parts):
+                cs = None
+            abi.groupnorm(x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu,
+                          colstats=cs)
         return y
 
     def ln(self, x, prefix):
@@ -426,7 +458,7 @@ class _Runner:
         return y
 
     def conv3x3(self, a, wname, bname, H, W, out_dtype, stride=1, up=False, residual=None, rowbias=None,
-                rowbias_rows=0, wdtype=None):
+                rowbias_rows=0, wdtype=None, out=None, stats=False):
         w = self.conv_w(wname, wdtype)
         n_img = a.shape[0] // (H * W)
         if up and self.use_tc and wdtype is None:
@@ -441,27 +473,30 @@ class _Runner:
         oh, ow = (eh - 1) // stride + 1, (ew - 1) // stride + 1
         return self.gemm(a, w, w.shape[0], out_dtype, bias=self.vec(bname), residual=residual, rowbias=rowbias,
                          rowbias_rows=rowbias_rows, mode=abi.A_CONV3X3, conv=(cin, H, W, oh, ow, stride, int(up)),
-                         M=n_img * oh * ow, tc_ok=(wdtype is None))
+                         M=n_img * oh * ow, tc_ok=(wdtype is None), out=out, stats=stats)
 
-    def convt3(self, a, wname, bname, frame_rows, out_dtype, residual=None):
+    def convt3(self, a, wname, bname, frame_rows, out_dtype, residual=None, out=None, stats=False):
         w = self.conv_w(wname)
         return self.gemm(a, w, w.shape[0], out_dtype, bias=self.vec(bname), residual=residual,
-                         mode=abi.A_CONVT3, convt=(a.shape[1], self.Tf, frame_rows))
+                         mode=abi.A_CONVT3, convt=(a.shape[1], self.Tf, frame_rows), out=out, stats=stats)
 
     # ---- blocks -------------------------------------------------------------------------------
-    def res_block(self, blk, x, H, W):
+    def res_block(self, blk, x, H, W, out=None):
+        """out: where the block's result should land (a trunk tensor or column slice), when the producing kernel
+        can write there directly; the caller copies otherwise."""
         p = blk._pfx
         rows_per_sample = self.T * H * W
         a = self.gn(x, p + "in_layers.0.", self.b * self.T, 1e-5, True)
         off, n = self.emb_slices[p]
         h = self.conv3x3(a, p + "in_layers.2.weight", p + "in_layers.2.bias", H, W, torch.float32,
-                         rowbias=self.emb_all[:, off:off + n], rowbias_rows=rows_per_sample)
+                         rowbias=self.emb_all[:, off:off + n], rowbias_rows=rows_per_sample, stats=True)
         a = self.gn(h, p + "out_layers.0.", self.b * self.T, 1e-5, True)
         if isinstance(blk.skip_connection, nn.Identity):
             skip = x
         else:
             skip = self.linear(x, p + "skip_connection.weight", p + "skip_connection.bias", torch.float32)
-        h = self.conv3x3(a, p + "out_layers.3.weight", p + "out_layers.3.bias", H, W, torch.float32, residual=skip)
+        h = self.conv3x3(a, p + "out_layers.3.weight", p + "out_layers.3.bias", H, W, torch.float32, residual=skip,
+                         stats=True, out=None if blk.use_temporal_conv else out)
         if blk.use_temporal_conv:
             q = p + "temopral_conv."
             hw = H * W
@@ -472,7 +507,8 @@ class _Runner:
             for i, ci in ((1, 2), (2, 3), (3, 3), (4, 3)):
                 a = self.gn(y, f"{q}conv{i}.0.", self.b, 1e-5, True, clip_wide=True)
                 y = self.convt3(a, f"{q}conv{i}.{ci}.weight", f"{q}conv{i}.{ci}.bias", hw, torch.float32,
-                                residual=h if i == 4 else None)
+                                residual=h if i == 4 else None, stats=True,
+                                out=out if (i == 4 and self.sp is None) else None)
             h = y if self.sp is None else self.sp.pixels_to_frames(y, self.T, H * W)
         return h
 
@@ -535,7 +571,7 @@ class _Runner:
             t = self._ff_out(blk, g, t, self.opdt if i == nb - 1 else torch.float32)
         return t
 
-    def spatial_transformer(self, mod, x, H, W):
+    def spatial_transformer(self, mod, x, H, W, out=None):
         p = mod._pfx
         HW = H * W
         a = self.gn(x, p + "norm.", self.b * self.T, 1e-6, False)
@@ -544,9 +580,9 @@ class _Runner:
                     op=lambda ten, off, ld: abi.operand(ten, 1, HW * ld, 0, ld, off),
                     o=lambda ld: (1, HW * ld, 0, ld))
         t = self._blocks(mod, t, mod.n_heads, addr, self.ctx_kv)
-        return self.linear(t, p + "proj_out.weight", p + "proj_out.bias", torch.float32, residual=x)
+        return self.linear(t, p + "proj_out.weight", p + "proj_out.bias", torch.float32, residual=x, stats=True, out=out)
 
-    def temporal_transformer(self, mod, x, H, W):
+    def temporal_transformer(self, mod, x, H, W, out=None):
         """Rows stay in (b, t, p) order; attention gathers the T frames of a pixel by stride."""
         p = mod._pfx
         HW, T = H * W, self.Tf
@@ -559,7 +595,8 @@ class _Runner:
                     op=lambda ten, off, ld: abi.operand(ten, HW, T * HW * ld, ld, HW * ld, off),
                     o=lambda ld: (HW, T * HW * ld, ld, HW * ld))
         t = self._blocks(mod, t, mod.n_heads, addr, None)
-        y = self.linear(t, p + "proj_out.weight", p + "proj_out.bias", torch.float32, residual=x)
+        y = self.linear(t, p + "proj_out.weight", p + "proj_out.bias", torch.float32, residual=x, stats=True,
+                        out=out if self.sp is None else None)
         return y if self.sp is None else self.sp.pixels_to_frames(y, self.T, H * W)
 
     # ---- conditioning -------------------------------------------------------------------------
@@ -657,26 +694,49 @@ class _Runner:
             off += c
 
     # ---- the walk -----------------------------------------------------------------------------
-    def run_block(self, seq, h, H, W):
-        for layer in seq:
+    def run_block(self, seq, h, H, W, out=None):
+        """out: destination of the block's final result (half of a skip-concatenation buffer); the last layer
+        writes there directly when it can."""
+        last = len(seq) - 1
+        for idx, layer in enumerate(seq):
+            o = out if idx == last else None
             if isinstance(layer, ResBlock):
-                h = self.res_block(layer, h, H, W)
+                h = self.res_block(layer, h, H, W, out=o)
             elif isinstance(layer, SpatialTransformer):
-                h = self.spatial_transformer(layer, h, H, W)
+                h = self.spatial_transformer(layer, h, H, W, out=o)
             elif isinstance(layer, TemporalTransformer):
-                h = self.temporal_transformer(layer, h, H, W)
+                h = self.temporal_transformer(layer, h, H, W, out=o)
             elif isinstance(layer, Downsample):
-                h = self.conv3x3(h, layer._pfx + "op.weight", layer._pfx + "op.bias", H, W, torch.float32, stride=2)
+                h = self.conv3x3(h, layer._pfx + "op.weight", layer._pfx + "op.bias", H, W, torch.float32, stride=2,
+                                 stats=True, out=o)
                 H, W = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             elif isinstance(layer, Upsample):
-                h = self.conv3x3(h, layer._pfx + "conv.weight", layer._pfx + "conv.bias", H, W, torch.float32, up=True)
+                h = self.conv3x3(h, layer._pfx + "conv.weight", layer._pfx + "conv.bias", H, W, torch.float32, up=True,
+                                 stats=True, out=o)
                 H, W = 2 * H, 2 * W
             elif isinstance(layer, nn.Conv2d):   # the 8 -> 320 stem: always exact fp32
                 h = self.conv3x3(h, layer._pfx + "weight", layer._pfx + "bias", H, W, torch.float32,
-                                 wdtype=torch.float32)
+                                 wdtype=torch.float32, out=o)
             else:
                 raise TypeError(type(layer))
+        if out is not None and h is not out:
+            abi.copy_rows(h, out)
+            out._cs_valid = False
+            h = out
         return h, H, W
+
+    @staticmethod
+    def _seq_out_channels(seq):
+        for layer in reversed(list(seq)):
+            if isinstance(layer, ResBlock):
+                return layer.out_channels
+            if isinstance(layer, (Downsample, Upsample)):
+                return layer.channels
+            if isinstance(layer, nn.Conv2d):
+                return layer.out_channels
+            if isinstance(layer, (SpatialTransformer, TemporalTransformer)):
+                return layer.in_channels
+        raise TypeError("empty block")
 
     def run(self):
         m, x = self.m, self.x
@@ -706,20 +766,31 @@ class _Runner:
             raise RuntimeError("in_channels must be a multiple of 4")
         h = self.new(b * T * H * W, cin, torch.float32)
         abi.video_to_rows(xin, x2, h, b, T, H * W)
-        hs = []
+        # Skip concatenations (openaimodel3d.py:600: h = cat([h, hs.pop()], 1)) are never copied: the buffer of
+        # decoder block k is allocated when encoder block (n-1-k) runs, the encoder writes its result into the
+        # right-hand columns, the preceding decoder block (or the middle block) into the left-hand ones.
+        n_dec = len(m.output_blocks)
+        assert n_dec == len(m.input_blocks)
+        cats = [None] * n_dec
         for i, seq in enumerate(m.input_blocks):
-            h, H, W = self.run_block(seq, h, H, W)
+            k = n_dec - 1 - i
+            Ho, Wo = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if any(isinstance(l, Downsample) for l in seq) else (H, W)
+            c_tot, c_s = m.output_blocks[k][0].channels, self._seq_out_channels(seq)
+            cat = self.new_trunk(b * T * Ho * Wo, c_tot)
+            hv, sv = self.trunk_cols(cat, 0, c_tot - c_s), self.trunk_cols(cat, c_tot - c_s, c_tot)
+            cat._cs_parts = [hv, sv]
+            cats[k] = (cat, hv, sv)
             if i == 0 and m.addition_attention:
-                h, H, W = self.run_block(m.init_attn, h, H, W)
-            hs.append((h, H, W))
-        h, H, W = self.run_block(m.middle_block, h, H, W)
-        for seq in m.output_blocks:
-            s, sh, sw = hs.pop()
-            assert (sh, sw) == (H, W)
-            cat = self.new(h.shape[0], h.shape[1] + s.shape[1], torch.float32)
-            abi.copy_rows(h, cat[:, :h.shape[1]])
-            abi.copy_rows(s, cat[:, h.shape[1]:])
-            h, H, W = self.run_block(seq, cat, H, W)
+                h, H, W = self.run_block(seq, h, H, W)
+                h, H, W = self.run_block(m.init_attn, h, H, W, out=sv)
+            else:
+                h, H, W = self.run_block(seq, h, H, W, out=sv)
+        h, H, W = self.run_block(m.middle_block, h, H, W, out=cats[0][1])
+        for k, seq in enumerate(m.output_blocks):
+            cat, hv, sv = cats[k]
+            cats[k] = None
+            assert h is hv and cat.shape[0] == b * T * H * W
+            h, H, W = self.run_block(seq, cat, H, W, out=cats[k + 1][1] if k + 1 < n_dec else None)
         if self.use_tc:
             # 320 -> 4 head conv on the tensor cores: output channels zero-padded to one 16-wide UMMA tile
             oc = m.out_channels

@@ -82,8 +82,8 @@ def test_tc_conv3x3_declines_what_it_cannot_tile(abi):
     rows = rnd(16 * 2 * 2, 64, seed=16, dtype=BF)
     w = rnd(64, 9 * 64, seed=17, dtype=BF)
     c = torch.empty(64, 64, device="cuda")
-    assert abi.gemm(rows, w, c, mode=abi.A_CONV3X3, conv=(64, 2, 2, 2, 2, 1, 0), tc=True) is False
-    assert abi.gemm(rows, w, c, mode=abi.A_CONV3X3, conv=(64, 2, 2, 4, 4, 1, 1), tc=True, M=256) is False
+    assert abi.gemm(rows, w, c, mode=abi.A_CONV3X3, conv=(64, 2, 2, 2, 2, 1, 0), tc=True) == 0
+    assert abi.gemm(rows, w, c, mode=abi.A_CONV3X3, conv=(64, 2, 2, 4, 4, 1, 1), tc=True, M=256) == 0
 
 
 @pytest.mark.parametrize("b,T,HW,C", [(1, 16, 160, 320), (2, 16, 64, 64), (1, 16, 40, 1280), (1, 16, 2560, 64),
@@ -173,3 +173,63 @@ def test_tc_conv3x3_stride2_by_tma_element_strides(abi, n, cin, cout, H, W):
     ok = abi.gemm(rows, conv_weight_rows(w), c, bias=bias, mode=abi.A_CONV3X3, conv=(cin, H, W, oh, ow, 2, 0), tc=True)
     assert ok
     assert rel_l2(c, ref.permute(0, 2, 3, 1).reshape(n * oh * ow, cout)) < 1e-5
+
+
+def _slab_stats(c):
+    """fp64 reference of pb_gemm_args.colstats: per 32-row slab, per column (sum, sumsq)."""
+    M, N = c.shape
+    v = c.double().reshape(M // 32, 32, N)
+    return torch.stack([v.sum(1), (v * v).sum(1)], dim=-1).reshape(M // 32, 2 * N)
+
+
+@pytest.mark.parametrize("mode,shape", [("linear", (4096, 320, 320)), ("linear", (640, 1280, 320)),
+                                        ("conv", (4, 64, 320, 40, 64)), ("conv", (16, 128, 64, 20, 32)),
+                                        ("conv", (32, 64, 320, 10, 16)), ("convt", (2, 64, 2560)),
+                                        ("convt", (1, 128, 160))])
+def test_tc_gemm_colstats_and_fused_groupnorm(abi, mode, shape):
+    """The epilogue's column statistics equal a reduction of the stored output, and GroupNorm from them equals
+    GroupNorm from a pass over the tensor (also through a column slice of a wider buffer)."""
+    if mode == "linear":
+        M, N, K = shape
+        a, w = rnd(M, K, seed=41, dtype=BF), rnd(N, K, seed=42, dtype=BF, scale=K ** -0.5)
+        kw, n_inst = {}, 4
+    elif mode == "conv":
+        n, cin, N, H, W = shape
+        M, K = n * H * W, 9 * cin
+        a, w = rnd(M, cin, seed=41, dtype=BF), rnd(N, K, seed=42, dtype=BF, scale=K ** -0.5)
+        kw, n_inst = dict(mode=abi.A_CONV3X3, conv=(cin, H, W, H, W, 1, 0)), n
+    else:
+        nb, C, HW = shape
+        M, K, N = nb * 16 * HW, 3 * C, C
+        a, w = rnd(M, C, seed=41, dtype=BF), rnd(N, K, seed=42, dtype=BF, scale=K ** -0.5)
+        kw, n_inst = dict(mode=abi.A_CONVT3, convt=(C, 16, HW)), nb
+    bias, res = rnd(N, seed=43), rnd(M, N, seed=44)
+    wide = torch.zeros(M, N + 64, device="cuda")
+    wide_cs = torch.full((M // 32, 2 * (N + 64)), float("nan"), device="cuda")
+    c, cs = wide[:, 64:], wide_cs[:, 128:]
+    rc = abi.gemm(a, w, c, bias=bias, residual=res, tc=True, colstats=cs, **kw)
+    assert rc == 2, "expected the tcgen05 path to write column statistics for this shape"
+    ref = _slab_stats(c)
+    assert rel_l2(cs, ref) < 1e-5
+    assert torch.isnan(wide_cs[:, :128]).all()
+    # GroupNorm from the fused statistics == GroupNorm with its own statistics pass
+    gamma, beta = rnd(N, seed=45), rnd(N, seed=46)
+    rows = M // n_inst
+    y0 = torch.empty(M, N, dtype=BF, device="cuda")
+    y1 = torch.empty(M, N, dtype=BF, device="cuda")
+    abi.groupnorm(c, y0, n_inst, rows, gamma, beta, 1e-5, True)
+    abi.groupnorm(c, y1, n_inst, rows, gamma, beta, 1e-5, True, colstats=cs)
+    assert rel_l2(y1, y0.double()) < 2e-3
+    want = F.silu(F.group_norm(c.double().reshape(n_inst, rows, N).permute(0, 2, 1), 32, gamma.double(),
+                               beta.double(), 1e-5)).permute(0, 2, 1).reshape(M, N)
+    assert rel_l2(y1, want) < 4e-3
+
+
+def test_tc_gemm_colstats_declined(abi):
+    """Shapes whose tiles do not map to aligned 32-row slabs (5x8 images) or that use split-K report 1, not 2."""
+    n, cin, N, H, W = 16, 64, 64, 5, 8
+    M = n * H * W
+    a, w = rnd(M, cin, seed=41, dtype=BF), rnd(N, 9 * cin, seed=42, dtype=BF, scale=0.05)
+    c = torch.empty(M, N, device="cuda")
+    cs = torch.zeros(M // 32, 2 * N, device="cuda")
+    assert abi.gemm(a, w, c, tc=True, colstats=cs, mode=abi.A_CONV3X3, conv=(cin, H, W, H, W, 1, 0)) == 1
