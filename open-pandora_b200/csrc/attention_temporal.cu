@@ -7,6 +7,7 @@
 // joined with one shuffle; scores stay in registers (no online softmax needed for 16 keys).
 // Rows are read in place from the (b, t, p)-ordered activation through the generic pb_attn_operand strides.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -114,6 +115,154 @@ __global__ void __launch_bounds__(32 * T_WARPS) attn_small_kernel(SmallAttnP p) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// bf16 fast path: the same warp-per-(pixel, head) decomposition, but Q / K / V (16 x 64 bf16 = 2 KB each) are
+// staged with cp.async (16 B per lane, all 12 copies of a warp in flight at once, no register staging), and the
+// two 16x16x64 / 16x64x16 products run on mma.sync m16n8k16 (a 16-token sequence is far below the 128-row
+// tcgen05 tile; the op is HBM-bound and the point of the tensor-core path is to take the 1024 FMAs per lane
+// off the issue slots so that the loads set the pace).  Scores never leave registers: the S accumulator
+// fragments are exactly the A fragments of the P.V product.  O is staged through the (dead) Q tile so the
+// global stores are 16 B per lane.
+constexpr int TM_WARPS = 8;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;      // src-size 0 => zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(32 * TM_WARPS) attn_small_mma_kernel(SmallAttnP p) {
+  // per warp: Q, K, V tiles [16 rows][64 bf16] = 128 B rows, 16-byte chunk c of row j stored at chunk c ^ (j & 7)
+  __shared__ __align__(128) uint8_t tiles[TM_WARPS][3][TS_MAX * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t grp = (int64_t)blockIdx.x * TM_WARPS + warp;
+  if (grp >= p.batch * p.heads) return;
+  const int64_t n = grp / p.heads;
+  const int h = (int)(grp - n * p.heads);
+  const bf16* Q = reinterpret_cast<const bf16*>(p.q) + (n / p.q_bdiv) * p.q_bso + (n % p.q_bdiv) * p.q_bsi + h * TD;
+  const bf16* K = reinterpret_cast<const bf16*>(p.k) + (n / p.k_bdiv) * p.k_bso + (n % p.k_bdiv) * p.k_bsi + h * TD;
+  const bf16* V = reinterpret_cast<const bf16*>(p.v) + (n / p.v_bdiv) * p.v_bso + (n % p.v_bdiv) * p.v_bsi + h * TD;
+  const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(&tiles[warp][0][0]);
+  const uint32_t sK = sQ + TS_MAX * 128, sV = sK + TS_MAX * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = lane + 32 * i, j = e >> 3, c = e & 7;
+    const uint32_t off = (uint32_t)(j * 128 + ((c ^ (j & 7)) << 4));
+    const bool ok = j < p.n;
+    cp_async16(sQ + off, Q + (int64_t)j * p.q_rs + c * 8, ok);
+    cp_async16(sK + off, K + (int64_t)j * p.k_rs + c * 8, ok);
+    cp_async16(sV + off, V + (int64_t)j * p.v_rs + c * 8, ok);
+  }
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  // ---- S = Q K^T : two n-tiles (keys 0-7, 8-15), four k-steps over d
+  float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4], b[4];
+    {
+      const int row = lane & 15, c = 2 * ks + (lane >> 4);
+      ldsm_x4(sQ + (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)), a);
+    }
+    {
+      const int key = ((lane >> 4) << 3) + (lane & 7), c = 2 * ks + ((lane >> 3) & 1);
+      ldsm_x4(sK + (uint32_t)(key * 128 + ((c ^ (key & 7)) << 4)), b);
+    }
+    mma_bf16_16816(s0, a, b[0], b[1]);
+    mma_bf16_16816(s1, a, b[2], b[3]);
+  }
+  // ---- softmax over the 16 keys of rows g = lane/4 and g + 8; a thread holds keys {2t, 2t+1, 8+2t, 9+2t}
+  const int t2 = (lane & 3) * 2;
+  const float NEG = -INFINITY;
+  float v0[4] = {s0[0], s0[1], s1[0], s1[1]};      // row g
+  float v1[4] = {s0[2], s0[3], s1[2], s1[3]};      // row g + 8
+  const int keys[4] = {t2, t2 + 1, 8 + t2, 9 + t2};
+  float m0 = NEG, m1 = NEG;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v0[i] = keys[i] < p.n ? v0[i] * p.scale_log2 : NEG;
+    v1[i] = keys[i] < p.n ? v1[i] * p.scale_log2 : NEG;
+    m0 = fmaxf(m0, v0[i]); m1 = fmaxf(m1, v1[i]);
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v0[i] = exp2f(v0[i] - m0); l0 += v0[i];
+    v1[i] = exp2f(v1[i] - m1); l1 += v1[i];
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+  // P as the A fragment of the second product (normalised first, so O needs no rescale)
+  uint32_t pa[4] = {pack_bf16x2(v0[0] * inv0, v0[1] * inv0), pack_bf16x2(v1[0] * inv1, v1[1] * inv1),
+                    pack_bf16x2(v0[2] * inv0, v0[3] * inv0), pack_bf16x2(v1[2] * inv1, v1[3] * inv1)};
+  // ---- O = P V : eight n-tiles of 8 head-dim columns, one k-step (16 keys); V is [key][d] -> transposed ldmatrix
+  float o[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+#pragma unroll
+  for (int np = 0; np < 4; ++np) {
+    uint32_t b[4];
+    const int key = (lane & 7) + (((lane >> 3) & 1) << 3), c = 2 * np + (lane >> 4);
+    ldsm_x4_t(sV + (uint32_t)(key * 128 + ((c ^ (key & 7)) << 4)), b);
+    mma_bf16_16816(o[2 * np], pa, b[0], b[1]);
+    mma_bf16_16816(o[2 * np + 1], pa, b[2], b[3]);
+  }
+  // ---- stage O (bf16) through the Q tile, then 16-byte coalesced stores
+  __syncwarp();
+  const int g = lane >> 2;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    // columns nt*8 + t2, +1 -> chunk nt, byte offset t2*2 inside the chunk
+    const uint32_t a0 = sQ + (uint32_t)(g * 128 + ((nt ^ (g & 7)) << 4) + t2 * 2);
+    const uint32_t a1 = sQ + (uint32_t)((g + 8) * 128 + ((nt ^ ((g + 8) & 7)) << 4) + t2 * 2);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0), "r"(pack_bf16x2(o[nt][0], o[nt][1])) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1), "r"(pack_bf16x2(o[nt][2], o[nt][3])) : "memory");
+  }
+  __syncwarp();
+  bf16* O = reinterpret_cast<bf16*>(p.out) + (n / p.o_bdiv) * p.o_bso + (n % p.o_bdiv) * p.o_bsi + h * TD;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int e = lane + 32 * i, j = e >> 3, c = e & 7;
+    if (j >= p.n) continue;
+    uint4 val;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                 : "r"(sQ + (uint32_t)(j * 128 + ((c ^ (j & 7)) << 4))));
+    uint4* dst = reinterpret_cast<uint4*>(O + (int64_t)j * p.o_rs + c * 8);
+    if (p.accumulate) {
+      const uint4 prev = *dst;
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&val);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&prev);
+      uint32_t r[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        r[q] = pack_bf16x2(__low2float(a2[q]) + __low2float(b2[q]), __high2float(a2[q]) + __high2float(b2[q]));
+      val = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+    *dst = val;
+  }
+}
+
 // called by pb_attention for n_q == n_kv <= 16
 int launch_small_attention(const pb_attn_args* a, cudaStream_t st) {
   SmallAttnP p;
@@ -128,8 +277,22 @@ int launch_small_attention(const pb_attn_args* a, cudaStream_t st) {
   const int64_t groups = a->batch * a->heads;
   const int64_t blocks = ceil_div(groups, T_WARPS);
   PB_REQUIRE(blocks <= 2147483647LL, "pb_attention: grid too large");
-  if (a->dtype == PB_F32) attn_small_kernel<float><<<(unsigned)blocks, 32 * T_WARPS, 0, st>>>(p);
-  else attn_small_kernel<bf16><<<(unsigned)blocks, 32 * T_WARPS, 0, st>>>(p);
+  if (a->dtype == PB_F32) {
+    attn_small_kernel<float><<<(unsigned)blocks, 32 * T_WARPS, 0, st>>>(p);
+  } else {
+    // tensor-core path needs 16-byte addressable rows (every stride a multiple of 8 bf16, 16-byte aligned bases)
+    const int64_t strides = a->q.bs_outer | a->q.bs_inner | a->q.rs | a->k.bs_outer | a->k.bs_inner | a->k.rs |
+                            a->v.bs_outer | a->v.bs_inner | a->v.rs | a->o_bs_outer | a->o_bs_inner | a->o_rs;
+    const uintptr_t ptrs = reinterpret_cast<uintptr_t>(a->q.ptr) | reinterpret_cast<uintptr_t>(a->k.ptr) |
+                           reinterpret_cast<uintptr_t>(a->v.ptr) | reinterpret_cast<uintptr_t>(a->out);
+    static const bool mma_on = []() { const char* e = getenv("PB_TEMPORAL_MMA"); return !(e && e[0] == '0'); }();
+    if (mma_on && strides % 8 == 0 && (ptrs & 15) == 0) {
+      const int64_t blocks8 = ceil_div(groups, TM_WARPS);
+      attn_small_mma_kernel<<<(unsigned)blocks8, 32 * TM_WARPS, 0, st>>>(p);
+    } else {
+      attn_small_kernel<bf16><<<(unsigned)blocks, 32 * T_WARPS, 0, st>>>(p);
+    }
+  }
   PB_LAUNCH_CHECK("attn_small_kernel");
   return PB_OK;
 }

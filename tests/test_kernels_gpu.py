@@ -195,6 +195,22 @@ def test_attention_temporal_in_place_layout(abi, dtype):
     assert rel_l2(out, ref) < tol(dtype)
 
 
+@pytest.mark.parametrize("T,HW,heads", [(16, 40, 5), (8, 24, 2), (5, 17, 1), (16, 2560, 5)])
+def test_attention_temporal_bf16_short_and_ragged(abi, T, HW, heads):
+    """mma.sync temporal kernel: sequences shorter than 16 (key masking, rows not stored) and odd pixel counts."""
+    b, C = 1, heads * 64
+    qkv = rnd(b * T * HW, 3 * C, seed=35, dtype=torch.bfloat16)
+    out = torch.full((b * T * HW, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    ld = 3 * C
+    op = lambda off: abi.operand(qkv, HW, T * HW * ld, ld, HW * ld, off)
+    abi.attention(op(0), op(C), op(2 * C), out, (HW, T * HW * C, C, HW * C), b * HW, heads, T, T, 0.125, abi.BF16)
+    x = qkv.reshape(b, T, HW, 3 * C).permute(0, 2, 1, 3).reshape(b * HW, T, 3 * C)
+    ref = ref_attn(x[..., :C], x[..., C:2 * C], x[..., 2 * C:], heads)
+    ref = ref.reshape(b, HW, T, C).permute(0, 2, 1, 3).reshape(b * T * HW, C)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < tol(torch.bfloat16)
+
+
 # ----------------------------------------------------------------------------------- small ops
 def test_geglu_silu_add_copy(abi):
     u = rnd(37, 256, seed=40)
