@@ -165,9 +165,16 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--res", default="512", choices=["512", "1024"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sp", type=int, default=1, help="sequence-parallel ways: ONE clip across this many ranks "
+                    "(frames sharded for spatial layers, NCCL all-to-all to pixel shards for temporal layers)")
+    ap.add_argument("--cfg-par", type=int, default=1, choices=[1, 2],
+                    help="2 = the cond / uncond branches of a step on two ranks (one all-gather of v per step)")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if os.environ.get("PB_BENCH_WATCHDOG"):       # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["PB_BENCH_WATCHDOG"]), exit=True)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -184,6 +191,20 @@ def main():
     abi.load()
 
     unet, model, sampler, inp, latent, ucfg = build_native(args.res, dev)
+    clip_ways = args.sp * args.cfg_par            # ranks that cooperate on one clip
+    if world % clip_ways:
+        raise SystemExit(f"world size {world} is not divisible by sp*cfg_par = {clip_ways}")
+    n_clips = world // clip_ways                  # independent clips in flight (data-parallel replicas)
+    if clip_ways > 1:
+        from pandora_b200.dist import CFGParallel, SequenceParallel, make_groups
+        from pandora_b200.synthetic import synth_inputs
+        dp_index, cfg_group, sp_group, rep_group = make_groups(world, args.cfg_par, args.sp)
+        inp = synth_inputs(1, latent, ucfg["context_dim"], seed=dp_index)      # the same clip on all its ranks
+        if args.sp > 1:
+            unet.sequence_parallel = SequenceParallel(sp_group)
+        if args.cfg_par > 1:
+            sampler.cfg_parallel = CFGParallel(cfg_group)
+        sampler.replica_group = rep_group
     b = 1
     shape = (b, *latent)
     d = {k: v.to(dev) for k, v in inp.items()}
@@ -239,7 +260,7 @@ def main():
     ms_total, launches = timed(one_step, args.warmup, args.steps)
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
-    value = world * 1e3 / ms_step
+    value = n_clips * 1e3 / ms_step
 
     # ---- e2e: public sampler objects, host (pinned) buffers, H2D/D2H inside the timed region
     host = {k: inp[k].pin_memory() for k in ("x", "c_concat", "context", "uc_context")}
@@ -273,6 +294,11 @@ def main():
 
     # ---- instrumented eager step: per-launch CUDA events -> breakdown + roofline of the GEMM family
     breakdown, roofline = None, None
+    if rank != 0 and clip_ways > 1:               # the step contains collectives: every rank of the clip runs it
+        g.step_index.zero_()
+        g.ts.fill_(steps_ddpm[0])
+        g._body()
+        torch.cuda.synchronize()
     if rank == 0:
         g.step_index.zero_()
         g.ts.fill_(steps_ddpm[0])
@@ -296,7 +322,7 @@ def main():
                             traffic=None, launches_per_step=n, avg_launch_us=round(ms / n * 1e3, 2),
                             flops_per_launch=fl / n, share_of_step=round(ms / tot, 4), peak_source=pk["src"] + " sustained",
                             how="per-launch CUDA events on the launching stream, instrumented eager step after the timed region")
-        whole = 2 * FLOP_PER_FORWARD[args.res] / (ms_step * 1e-3) / 1e12
+        whole = 2 * FLOP_PER_FORWARD[args.res] / (ms_step * 1e-3) / 1e12 / clip_ways     # per GPU
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import unet_oracle
@@ -308,22 +334,35 @@ def main():
                             sample=f"1 fp32 oracle U-Net forward at the full latent ({sec:.1f} s, no warm-up); "
                                    "a CFG step = 2 forwards")
     if rank == 0:
-        line = dict(metric=METRIC, value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+        line = dict(metric=METRIC if args.res == "512" else METRIC.replace("320x512", "576x1024"), value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak" if clip_ways == 1 else "strong",
+                    vs_baseline=None, dtype="bf16",
                     data="synthetic",
                     config=dict(workload="DynamiCrafter 320x512 16-frame 50-step DDIM, CFG 7.5, guidance_rescale 0.7, "
                                          "eta 1.0, uniform_trailing; step = 2 U-Net forwards + fused CFG/DDIM update"
                                 if args.res == "512" else "DynamiCrafter 576x1024 16-frame CFG DDIM step",
-                                latent=list(latent), context=[333, 1024], clips_per_gpu=1, parallelism=f"dp{world}",
+                                latent=list(latent), context=[333, 1024], clips_in_flight=n_clips,
+                                parallelism=f"dp{n_clips}" + (f"xcfg{args.cfg_par}" if args.cfg_par > 1 else "")
+                                + (f"xsp{args.sp}" if args.sp > 1 else ""),
                                 params=1438854980, cuda_graph=not args.no_graph,
                                 l2="working set per step (2.9 GB bf16 weights + activations) exceeds the 126 MB L2"),
-                    e2e=dict(value=world * 1e3 / e2e_ms_step, unit="steps/s", h2d_bytes_per_step=h2d,
+                    e2e=dict(value=n_clips * 1e3 / e2e_ms_step, unit="steps/s", h2d_bytes_per_step=h2d,
                              d2h_bytes_per_step=d2h, ms_per_step=e2e_ms_step),
                     gpu_launches=launches, clocks=clk, roofline=roofline, cpu_baseline=cpu_baseline,
                     whole_step_tflops=round(whole, 1), whole_step_frac_of_peak=round(whole / peaks()["bf16"], 4),
                     sec_per_50_step_clip=round(S_DDIM * ms_step * 1e-3, 3), breakdown=breakdown)
         print(json.dumps(line), flush=True)
     if world > 1:
+        if clip_ways > 1:
+            # the captured CUDA graph holds NCCL kernels of the clip's communicators: tearing the process group
+            # down underneath it blocks forever; release the graph first, and do not let teardown hang the run
+            g.graph = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
