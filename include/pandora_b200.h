@@ -174,6 +174,10 @@ typedef struct pb_attn_args {
   float scale;
   int32_t dtype;      /* q/k/v/out element type */
   int32_t accumulate;
+  /* > 0 (pb_tc_attention, n_kv <= 128): keys [0, kv_split) and [kv_split, n_kv) are two independent softmaxes whose
+     outputs are summed: out = softmax(q k_text^T) v_text + softmax(q k_img^T) v_img with the text and image K/V
+     rows concatenated (attention.py:128-142, image_cross_attention_scale = 1).  0 = one softmax. */
+  int32_t kv_split;
 } pb_attn_args;
 
 int pb_attention(const pb_attn_args* args, pb_stream_t stream);    /* CUDA-core path, any n_q/n_kv */

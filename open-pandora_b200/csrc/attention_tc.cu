@@ -1,16 +1,20 @@
 // attention_tc.cu — tcgen05 flash attention, head_dim 64, bf16 operands, fp32 softmax/accumulation.
 //
-// One CTA per (batch, head, 128-query tile); 192 threads, warp-specialised:
-//   warp 0      TMA producer : Q tile once, then K_j / V_j tiles (128 keys x 64) through a 3-stage ring
-//   warp 1      MMA issuer   : S_j = Q K_j^T  (UMMA 128x128x64, both operands K-major, -> TMEM, 2 buffers)
-//                              O_j = P_j V_j  (UMMA 128x64x128, A = P_j from shared memory, B = V_j used
-//                              MN-major straight from its row-major [key][d] tile, -> TMEM, 2 buffers)
-//   warps 2..5  softmax      : one thread per query row (a TMEM lane): two passes over S_j in TMEM
-//                              (row max, then p = exp2(s*scale - m)), P_j written to shared memory as the
-//                              swizzled bf16 A operand, O_j pulled from TMEM and folded into a register
-//                              accumulator with the online-softmax correction.
-// S_{j+1} is issued before the softmax of tile j finishes, so tensor and MUFU/ALU work overlap.
+// One CTA per (batch, head, PAIR of 128-query tiles); 320 threads, warp-specialised:
+//   warp 0      TMA producer : the two Q tiles once, then K_j / V_j tiles (128 keys x 64) through a 3-stage ring;
+//                              K/V are fetched once for both query tiles
+//   warp 1      MMA issuer   : S_t,j = Q_t K_j^T (UMMA 128x128x64, both operands K-major, -> TMEM, one buffer per
+//                              query tile) and O_t,j = P_t,j V_j (UMMA 128x64x128, A = P from shared memory,
+//                              B = V_j used MN-major straight from its row-major [key][d] tile, -> TMEM).
+//                              Issue order S_0,j+1 | PV_1,j | S_1,j+1 | PV_0,j+1 ... : while one query tile is in
+//                              its softmax the tensor pipe works for the other one (ping-pong).
+//   warps 2..5 / 6..9  softmax of query tile 0 / 1: one thread per query row (a TMEM lane): row max over S in
+//                              TMEM, fold of the previous O partial into a register accumulator with the
+//                              online-softmax correction, then p = exp2(s*scale - m) written to shared memory as
+//                              the swizzled bf16 A operand of the PV product.
 // Key masking handles n_kv that is not a multiple of 128 (77 text / 16 image tokens, 160, 40, ...).
+// kv_split > 0 (n_kv <= 128): keys [0, split) and [split, n_kv) are two independent softmaxes whose outputs are
+// summed — text + image cross-attention (attention.py:128-142) in one pass over one concatenated K/V tile.
 #include <math.h>
 #include <string.h>
 
@@ -21,12 +25,13 @@ namespace tc {
 
 constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64;
 constexpr int KV_STAGES = 3;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_QT = 2;                       // query tiles per CTA
+constexpr int ATT_THREADS = 64 + 128 * ATT_QT;  // 320
 constexpr int UMMA_K = 16;
 constexpr int TILE_BYTES = 128 * 64 * 2;      // 16 KiB: one [128 x 64] bf16 tile
 constexpr int P_BYTES = 2 * TILE_BYTES;       // [128 x 128] bf16 as two K-blocks
-constexpr int ATT_SMEM = TILE_BYTES * (1 + 2 * KV_STAGES) + 2 * P_BYTES;   // 176 KiB
-constexpr int S_COL0 = 0, O_COL0 = 256;       // TMEM columns: S buffers at 0/128, O buffers at 256/320
+constexpr int ATT_SMEM = TILE_BYTES * (ATT_QT + 2 * KV_STAGES) + ATT_QT * P_BYTES;   // 192 KiB
+constexpr int S_COL0 = 0, O_COL0 = 256;       // TMEM columns: S of query tile t at t*128, O at 256 + t*64
 
 struct AttP {
   void* out;
@@ -35,6 +40,7 @@ struct AttP {
   int nq, nkv, kv_tiles;
   float scale_log2;
   int accumulate;
+  int split;             // > 0: two softmax segments [0, split) and [split, nkv) inside ONE key tile
 };
 
 // MN-major B operand tile [k rows][64 contiguous n], 128-byte swizzle: 8-row K groups 1024 B apart.
@@ -87,28 +93,28 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const __grid_constant__ CUtensorMap tmV, const AttP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base;
-  auto sK = [&](int s) { return base + TILE_BYTES * (1 + s); };
-  auto sV = [&](int s) { return base + TILE_BYTES * (1 + KV_STAGES + s); };
-  auto sP = [&](int b) { return base + TILE_BYTES * (1 + 2 * KV_STAGES) + P_BYTES * b; };
+  auto sQ = [&](int t) { return base + TILE_BYTES * t; };
+  auto sK = [&](int s) { return base + TILE_BYTES * (ATT_QT + s); };
+  auto sV = [&](int s) { return base + TILE_BYTES * (ATT_QT + KV_STAGES + s); };
+  auto sP = [&](int t) { return base + TILE_BYTES * (ATT_QT + 2 * KV_STAGES) + P_BYTES * t; };
   const uint32_t bars = base + ATT_SMEM;
   const uint32_t q_full = bars;
   auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bars + 8u * (1 + KV_STAGES + s); };
-  auto s_full = [&](int b) { return bars + 8u * (1 + 2 * KV_STAGES + b); };
-  auto p_full = [&](int b) { return bars + 8u * (3 + 2 * KV_STAGES + b); };
-  auto o_full = [&](int b) { return bars + 8u * (5 + 2 * KV_STAGES + b); };
+  auto s_full = [&](int t) { return bars + 8u * (1 + 2 * KV_STAGES + t); };
+  auto p_full = [&](int t) { return bars + 8u * (3 + 2 * KV_STAGES + t); };
+  auto o_full = [&](int t) { return bars + 8u * (5 + 2 * KV_STAGES + t); };
   const uint32_t tmem_slot = bars + 8u * (7 + 2 * KV_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
+  const int q_tile0 = blockIdx.x * ATT_QT, head = blockIdx.y, n = blockIdx.z;
   const int n_tiles = p.kv_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(p_full(b), 128); mbar_init(o_full(b), 1); }
+    for (int t = 0; t < ATT_QT; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 128); mbar_init(o_full(t), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -123,8 +129,9 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, head * ATT_D, q_tile * ATT_BM, n / p.q_bdiv);
+      mbar_expect_tx(q_full, ATT_QT * TILE_BYTES);
+      for (int t = 0; t < ATT_QT; ++t)      // a tile past the last query row is zero-filled by the copy engine
+        tma_load_3d(sQ(t), &tmQ, q_full, head * ATT_D, (q_tile0 + t) * ATT_BM, n / p.q_bdiv);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % KV_STAGES;
         mbar_wait(kv_empty(s), ((j / KV_STAGES) & 1) ^ 1);
@@ -137,137 +144,205 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN);                 // K-major A and B
       const uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);     // B (= V) MN-major
-      const uint64_t q_desc = make_smem_desc_sw128(sQ);
-      auto issue_s = [&](int j) {
+      auto issue_s = [&](int t, int j) {
         const int s = j % KV_STAGES;
         mbar_wait(kv_full(s), (j / KV_STAGES) & 1);
         tc_fence_after();
+        const uint64_t q_desc = make_smem_desc_sw128(sQ(t));
         const uint64_t k_desc = make_smem_desc_sw128(sK(s));
-        const uint32_t d = tmem_base + S_COL0 + (uint32_t)(j & 1) * ATT_BN;
+        const uint32_t d = tmem_base + S_COL0 + (uint32_t)t * ATT_BN;
 #pragma unroll
         for (int k = 0; k < ATT_D / UMMA_K; ++k) umma_bf16(d, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full(j & 1));
+        umma_commit(s_full(t));
       };
       mbar_wait(q_full, 0);
-      issue_s(0);
-      if (n_tiles > 1) issue_s(1);
+      issue_s(0, 0);
+      issue_s(1, 0);
       for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % KV_STAGES, b = j & 1;
-        mbar_wait(p_full(b), (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + O_COL0 + (uint32_t)b * ATT_D;
+        const int s = j % KV_STAGES;
 #pragma unroll
-        for (int k = 0; k < ATT_BN / UMMA_K; ++k) {
-          // A: P block k/4 (16 KiB apart), 32 B per k-step inside the swizzled row; B: 16 key rows = 2 KiB per step
-          const uint64_t a_desc = make_smem_desc_sw128(sP(b) + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
-          const uint64_t b_desc = make_smem_desc_mn_sw128(sV(s) + k * 16 * 128);
-          umma_bf16(d, a_desc, b_desc, idesc_o, k != 0);
+        for (int t = 0; t < ATT_QT; ++t) {
+          // P_t,j is in shared memory (this also means S_t,j has been consumed and O_t,j-1 has been folded)
+          mbar_wait(p_full(t), j & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + O_COL0 + (uint32_t)t * ATT_D;
+#pragma unroll
+          for (int k = 0; k < ATT_BN / UMMA_K; ++k) {
+            // A: P block k/4 (16 KiB apart), 32 B per k-step inside the swizzled row; B: 16 key rows = 2 KiB per step
+            const uint64_t a_desc = make_smem_desc_sw128(sP(t) + (k >> 2) * TILE_BYTES) + 2 * (k & 3);
+            const uint64_t b_desc = make_smem_desc_mn_sw128(sV(s) + k * 16 * 128);
+            umma_bf16(d, a_desc, b_desc, idesc_o, k != 0);
+          }
+          umma_commit(o_full(t));
+          if (t == ATT_QT - 1) umma_commit(kv_empty(s));     // K_j / V_j are free once every product on them is done
+          if (j + 1 < n_tiles) issue_s(t, j + 1);
         }
-        umma_commit(o_full(b));
-        umma_commit(kv_empty(s));
-        if (j + 2 < n_tiles) issue_s(j + 2);
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax + output (warps 2..5)
+    // ---------------------------------------------------------------- softmax + output (warps 2..5: tile 0, 6..9: tile 1)
+    const int t = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t s_addr = lane_addr + S_COL0 + (uint32_t)t * ATT_BN;
+    const uint32_t o_addr = lane_addr + O_COL0 + (uint32_t)t * ATT_D;
+    const uint32_t p_row = sP(t) + (uint32_t)r * 128;
     float acc[ATT_D];
 #pragma unroll
     for (int i = 0; i < ATT_D; ++i) acc[i] = 0.f;
     float m_run = -INFINITY, m_acc = -INFINITY, l = 0.f;
 
-    auto fold_o = [&](int t, float m_t) {
-      mbar_wait(o_full(t & 1), (t >> 1) & 1);
+    auto fold_o = [&](int jt, float m_t) {
+      mbar_wait(o_full(t), jt & 1);
       tc_fence_after();
       const float corr = fast_exp2(m_acc - m_t);   // 0 on the first tile (m_acc = -inf)
       m_acc = m_t;
 #pragma unroll
       for (int c = 0; c < ATT_D; c += 32) {
         float o[32];
-        tmem_ld32(lane_addr + O_COL0 + (uint32_t)(t & 1) * ATT_D + c, o);
+        tmem_ld32(o_addr + c, o);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], corr, o[i]);
       }
     };
+    // 32 probabilities (keys c .. c+31 of the tile) -> the swizzled bf16 A operand of the PV product
+    auto store_p = [&](int c, const uint32_t (&w)[16]) {
+      const uint32_t blk = p_row + (uint32_t)(c >> 6) * TILE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t chunk = (uint32_t)(((c & 63) >> 3) + q);
+        const uint32_t addr = blk + ((chunk ^ (uint32_t)(r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * q]), "r"(w[4 * q + 1]),
+                     "r"(w[4 * q + 2]), "r"(w[4 * q + 3])
+                     : "memory");
+      }
+    };
 
-    float m_prev_tile = -INFINITY;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int b = j & 1;
-      const int valid = p.nkv - j * ATT_BN;       // keys of this tile that exist (>= 1)
-      mbar_wait(s_full(b), (j >> 1) & 1);
+    if (p.split > 0) {
+      // ---- two softmax segments in one key tile (text | image tokens): normalised probabilities go into P, the
+      // product is the final output
+      mbar_wait(s_full(t), 0);
       tc_fence_after();
-      const uint32_t s_addr = lane_addr + S_COL0 + (uint32_t)b * ATT_BN;
-      const bool full = valid >= ATT_BN;          // no key masking needed (all but the last tile)
-      float mx = -INFINITY;
+      const int sp = p.split, nk = p.nkv;
+      float mx1 = -INFINITY, mx2 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < ATT_BN; c += 64) {
-        float v0[32], v1[32];
-        tmem_ld32(s_addr + c, v0);
-        tmem_ld32(s_addr + c + 32, v1);
+      for (int c = 0; c < ATT_BN; c += 32) {
+        float v[32];
+        tmem_ld32(s_addr + c, v);
         tmem_ld_wait();
-        if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(v0[i], v1[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            mx = fmaxf(mx, (c + i < valid) ? v0[i] : -INFINITY);
-            mx = fmaxf(mx, (c + 32 + i < valid) ? v1[i] : -INFINITY);
-          }
+        for (int i = 0; i < 32; ++i) {
+          mx1 = fmaxf(mx1, (c + i < sp) ? v[i] : -INFINITY);
+          mx2 = fmaxf(mx2, (c + i >= sp && c + i < nk) ? v[i] : -INFINITY);
         }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      l *= fast_exp2(m_run - m_new);
-      m_run = m_new;
-      const uint32_t p_row = sP(b) + (uint32_t)r * 128;
-      float lsum = 0.f;
+      mx1 *= p.scale_log2; mx2 *= p.scale_log2;
+      float l1 = 0.f, l2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < ATT_BN; c += 32) {
+        float v[32];
+        tmem_ld32(s_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (c + i < sp) l1 += fast_exp2(fmaf(v[i], p.scale_log2, -mx1));
+          else if (c + i < nk) l2 += fast_exp2(fmaf(v[i], p.scale_log2, -mx2));
+        }
+      }
+      const float i1 = 1.0f / l1, i2 = 1.0f / l2;
 #pragma unroll
       for (int c = 0; c < ATT_BN; c += 32) {
         float v[32];
         tmem_ld32(s_addr + c, v);
         tmem_ld_wait();
         uint32_t w[16];
-        if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = fast_exp2(fmaf(v[i], p.scale_log2, -m_new));
-            const float p1 = fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new));
-            lsum += p0 + p1;
-            w[i >> 1] = pack_bf16(p0, p1);
+        for (int i = 0; i < 32; i += 2) {
+          float pr[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = c + i + u;
+            pr[u] = col < sp ? fast_exp2(fmaf(v[i + u], p.scale_log2, -mx1)) * i1
+                  : col < nk ? fast_exp2(fmaf(v[i + u], p.scale_log2, -mx2)) * i2 : 0.f;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c + i < valid) ? fast_exp2(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
-            const float p1 = (c + i + 1 < valid) ? fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new)) : 0.f;
-            lsum += p0 + p1;
-            w[i >> 1] = pack_bf16(p0, p1);
-          }
+          w[i >> 1] = pack_bf16(pr[0], pr[1]);
         }
-        // 32 keys = 64 B = 4 chunks of 16 B; K-block (c / 64), chunk index within the 128-byte row
-        const uint32_t blk = p_row + (uint32_t)(c >> 6) * TILE_BYTES;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t chunk = (uint32_t)(((c & 63) >> 3) + q);
-          const uint32_t addr = blk + ((chunk ^ (uint32_t)(r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * q]), "r"(w[4 * q + 1]),
-                       "r"(w[4 * q + 2]), "r"(w[4 * q + 3])
-                       : "memory");
-        }
+        store_p(c, w);
       }
-      l += lsum;
-      fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(p_full(b));
-      if (j > 0) fold_o(j - 1, m_prev_tile);
-      m_prev_tile = m_new;
+      mbar_arrive(p_full(t));
+      m_acc = 0.f;
+      fold_o(0, 0.f);           // corr = exp2(0) = 1 on a zero accumulator
+      l = 1.f;
+    } else {
+      float m_prev_tile = -INFINITY;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int valid = p.nkv - j * ATT_BN;       // keys of this tile that exist (>= 1)
+        mbar_wait(s_full(t), j & 1);
+        tc_fence_after();
+        const bool full = valid >= ATT_BN;          // no key masking needed (all but the last tile)
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < ATT_BN; c += 64) {
+          float v0[32], v1[32];
+          tmem_ld32(s_addr + c, v0);
+          tmem_ld32(s_addr + c + 32, v1);
+          tmem_ld_wait();
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(v0[i], v1[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              mx = fmaxf(mx, (c + i < valid) ? v0[i] : -INFINITY);
+              mx = fmaxf(mx, (c + 32 + i < valid) ? v1[i] : -INFINITY);
+            }
+          }
+        }
+        const float m_new = fmaxf(m_run, mx * p.scale_log2);
+        l *= fast_exp2(m_run - m_new);
+        m_run = m_new;
+        // the previous product of this query tile is complete: fold it, and P may be overwritten
+        if (j > 0) fold_o(j - 1, m_prev_tile);
+        float lsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < ATT_BN; c += 32) {
+          float v[32];
+          tmem_ld32(s_addr + c, v);
+          tmem_ld_wait();
+          uint32_t w[16];
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = fast_exp2(fmaf(v[i], p.scale_log2, -m_new));
+              const float p1 = fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new));
+              lsum += p0 + p1;
+              w[i >> 1] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = (c + i < valid) ? fast_exp2(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
+              const float p1 = (c + i + 1 < valid) ? fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new)) : 0.f;
+              lsum += p0 + p1;
+              w[i >> 1] = pack_bf16(p0, p1);
+            }
+          }
+          store_p(c, w);
+        }
+        l += lsum;
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        tc_fence_before();
+        mbar_arrive(p_full(t));
+        m_prev_tile = m_new;
+      }
+      fold_o(n_tiles - 1, m_prev_tile);
     }
-    fold_o(n_tiles - 1, m_prev_tile);
 
-    const int64_t qi = (int64_t)q_tile * ATT_BM + r;
+    const int64_t qi = (int64_t)(q_tile0 + t) * ATT_BM + r;
     if (qi < p.nq) {
       const float inv = 1.0f / l;
       bf16* O = reinterpret_cast<bf16*>(p.out) + (n / p.o_bdiv) * p.o_bso + (n % p.o_bdiv) * p.o_bsi + qi * p.o_rs +
@@ -344,15 +419,18 @@ extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
   p.kv_tiles = (int)ceil_div(a->n_kv, ATT_BN);
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.accumulate = a->accumulate;
+  p.split = a->kv_split;
 
   static bool configured = false;
   const size_t smem = ATT_SMEM + 1024 + 8 * (8 + 2 * KV_STAGES) + 16;
+  if (a->kv_split < 0 || (a->kv_split > 0 && (a->n_kv > ATT_BN || a->kv_split >= a->n_kv)))
+    ATT_UNSUPPORTED("pb_tc_attention: kv_split needs 0 < kv_split < n_kv <= 128");
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attention_kernel)");
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM), (unsigned)a->heads, (unsigned)a->batch);
+  dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM * ATT_QT), (unsigned)a->heads, (unsigned)a->batch);
   tc_attention_kernel<<<grid, ATT_THREADS, smem, to_stream(stream)>>>(tq, tk, tv, p);
   PB_LAUNCH_CHECK("tc_attention_kernel");
   return PB_OK;

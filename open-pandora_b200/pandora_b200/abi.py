@@ -47,7 +47,7 @@ class AttnArgs(C.Structure):
         ("q", AttnOperand), ("k", AttnOperand), ("v", AttnOperand), ("out", C.c_void_p),
         ("o_bdiv", C.c_int64), ("o_bs_outer", C.c_int64), ("o_bs_inner", C.c_int64), ("o_rs", C.c_int64),
         ("batch", C.c_int64), ("heads", C.c_int64), ("n_q", C.c_int64), ("n_kv", C.c_int64),
-        ("scale", C.c_float), ("dtype", C.c_int32), ("accumulate", C.c_int32),
+        ("scale", C.c_float), ("dtype", C.c_int32), ("accumulate", C.c_int32), ("kv_split", C.c_int32),
     ]
 
 
@@ -322,7 +322,7 @@ def operand(t, bdiv, bs_outer, bs_inner, rs, offset=0):
     return o
 
 
-def attention(q, k, v, out, o_addr, batch, heads, n_q, n_kv, scale, dtype, accumulate=False, tc=False):
+def attention(q, k, v, out, o_addr, batch, heads, n_q, n_kv, scale, dtype, accumulate=False, tc=False, kv_split=0):
     """q, k, v: AttnOperand; out: tensor; o_addr = (bdiv, bs_outer, bs_inner, rs)."""
     global launches
     a = AttnArgs()
@@ -330,7 +330,7 @@ def attention(q, k, v, out, o_addr, batch, heads, n_q, n_kv, scale, dtype, accum
     a.out = out.data_ptr()
     a.o_bdiv, a.o_bs_outer, a.o_bs_inner, a.o_rs = o_addr
     a.batch, a.heads, a.n_q, a.n_kv = batch, heads, n_q, n_kv
-    a.scale, a.dtype, a.accumulate = scale, dtype, int(accumulate)
+    a.scale, a.dtype, a.accumulate, a.kv_split = scale, dtype, int(accumulate), int(kv_split)
     lib = load()
     fn = lib.pb_tc_attention if tc else lib.pb_attention
     esz = 2 if dtype == BF16 else 4

@@ -543,7 +543,15 @@ class _Runner:
                 q = self.linear(a, pa + "to_q.weight", None, self.opdt)
                 kv = ctx_kv[pa]
                 first = True
-                for key in ("text", "image"):
+                if "comb" in kv and self.use_tc:
+                    t, n_split, n_kv = kv["comb"]
+                    ld = t.stride(0)
+                    k_op = abi.operand(t, 1, n_kv * ld, 0, ld, 0)
+                    v_op = abi.operand(t, 1, n_kv * ld, 0, ld, Cd)
+                    if abi.attention(addr["op"](q, 0, q.stride(0)), k_op, v_op, o_addr[0], o_addr[1], batch, heads, n_tok,
+                                     n_kv, 64 ** -0.5, abi.BF16, False, tc=True, kv_split=n_split):
+                        first = None
+                for key in (("text", "image") if first else ()):
                     if kv.get(key) is None:
                         continue
                     t, n_kv, bdiv = kv[key]
@@ -644,6 +652,16 @@ class _Runner:
                         e["image"] = (kvi, IMG_TOKENS, 1)       # own 16 tokens per frame
                     else:
                         e["image"] = (kvi, n_img_rows, T)       # one token set shared by the clip
+                    # tcgen05 path: text and image K|V rows of every frame side by side in ONE key tile, so that
+                    # attn2 is a single launch with two softmax segments (pb_attn_args.kv_split)
+                    n_i = e["image"][1]
+                    if self.use_tc and n_text + n_i <= 128:
+                        C2 = kv.shape[1]
+                        comb = old["comb"][0] if "comb" in old else self.new(b * T * (n_text + n_i), C2, self.opdt)
+                        cv = comb.view(b, T, n_text + n_i, C2)
+                        cv[:, :, :n_text] = kv.view(b, 1, n_text, C2)
+                        cv[:, :, n_text:] = kvi.view(b, T, n_i, C2) if per_frame else kvi.view(b, 1, n_i, C2)
+                        e["comb"] = (comb, n_text, n_text + n_i)
                 out[pa] = e
         out["__keepalive__"] = ctx   # pins the address so (data_ptr, version) stays a valid identity
         if reuse is not None:

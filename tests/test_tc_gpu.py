@@ -152,12 +152,31 @@ def test_tc_attention_text_kv_shared_across_frames(abi):
     assert rel_l2(out, ref_attn(q.reshape(b * T, nq, C), k, v, heads).reshape(-1, C)) < 6e-3
 
 
+@pytest.mark.parametrize("nq,heads", [(160, 2), (2560, 5), (100, 1)])
+def test_tc_attention_two_segment_cross(abi, nq, heads):
+    """kv_split: text (77) and image (16) keys of a frame in one tile, two softmaxes, outputs summed
+    (attention.py:128-142) == two separate attentions added."""
+    B, nt, ni = 4, 77, 16
+    C = heads * 64
+    q = rnd(B * nq, C, seed=36, dtype=BF)
+    kv = rnd(B * (nt + ni), 2 * C, seed=37, dtype=BF)
+    out = torch.full((B * nq, C), float("nan"), dtype=BF, device="cuda")
+    n = nt + ni
+    assert abi.attention(abi.operand(q, 1, nq * C, 0, C, 0), abi.operand(kv, 1, n * 2 * C, 0, 2 * C, 0),
+                         abi.operand(kv, 1, n * 2 * C, 0, 2 * C, C), out, (1, nq * C, 0, C), B, heads, nq, n, 0.125,
+                         abi.BF16, tc=True, kv_split=nt)
+    k3, v3 = kv[:, :C].reshape(B, n, C), kv[:, C:].reshape(B, n, C)
+    q3 = q.reshape(B, nq, C)
+    ref = ref_attn(q3, k3[:, :nt], v3[:, :nt], heads) + ref_attn(q3, k3[:, nt:], v3[:, nt:], heads)
+    assert rel_l2(out, ref.reshape(B * nq, C)) < 6e-3
+
+
 def test_tc_attention_declines_temporal_layout(abi):
     qkv = rnd(16 * 24, 3 * 64, seed=34, dtype=BF)
     out = torch.empty(16 * 24, 64, dtype=BF, device="cuda")
     op = lambda off: abi.operand(qkv, 24, 16 * 24 * 192, 192, 24 * 192, off)
     assert abi.attention(op(0), op(64), op(128), out, (24, 16 * 24 * 64, 64, 24 * 64), 24, 1, 16, 16, 0.125,
-                         abi.BF16, tc=True) is False
+                         abi.BF16, tc=True) in (False, 0)
 
 
 @pytest.mark.parametrize("n,cin,cout,H,W", [(16, 64, 64, 8, 16), (2, 320, 320, 40, 64), (16, 640, 640, 20, 32),
