@@ -193,19 +193,22 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < ATT_D; ++i) acc[i] = 0.f;
     float m_run = -INFINITY, m_acc = -INFINITY, l = 0.f;
 
+    // TMEM loads are asynchronous until tcgen05.wait::ld: every loop below issues the load of the next chunk
+    // before it works on the current one, so the tensor-memory round trip hides behind the ALU / MUFU work
     auto fold_o = [&](int jt, float m_t) {
       mbar_wait(o_full(t), jt & 1);
       tc_fence_after();
       const float corr = fast_exp2(m_acc - m_t);   // 0 on the first tile (m_acc = -inf)
       m_acc = m_t;
+      float o0[32], o1[32];
+      tmem_ld32(o_addr, o0);
+      tmem_ld_wait();
+      tmem_ld32(o_addr + 32, o1);
 #pragma unroll
-      for (int c = 0; c < ATT_D; c += 32) {
-        float o[32];
-        tmem_ld32(o_addr + c, o);
-        tmem_ld_wait();
+      for (int i = 0; i < 32; ++i) acc[i] = fmaf(acc[i], corr, o0[i]);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], corr, o[i]);
-      }
+      for (int i = 0; i < 32; ++i) acc[32 + i] = fmaf(acc[32 + i], corr, o1[i]);
     };
     // 32 probabilities (keys c .. c+31 of the tile) -> the swizzled bf16 A operand of the PV product
     auto store_p = [&](int c, const uint32_t (&w)[16]) {
@@ -284,23 +287,33 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(s_full(t), j & 1);
         tc_fence_after();
         const bool full = valid >= ATT_BN;          // no key masking needed (all but the last tile)
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < ATT_BN; c += 64) {
+        float mx;
+        {
+          // four independent running maxima: a single fmaxf chain over 128 values is 128 dependent instructions
+          float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           float v0[32], v1[32];
-          tmem_ld32(s_addr + c, v0);
-          tmem_ld32(s_addr + c + 32, v1);
-          tmem_ld_wait();
-          if (full) {
+          auto take = [&](int c, const float (&v)[32]) {
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(v0[i], v1[i]));
-          } else {
+              for (int i = 0; i < 32; ++i) mq[i & 3] = fmaxf(mq[i & 3], v[i]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              mx = fmaxf(mx, (c + i < valid) ? v0[i] : -INFINITY);
-              mx = fmaxf(mx, (c + 32 + i < valid) ? v1[i] : -INFINITY);
+              for (int i = 0; i < 32; ++i) mq[i & 3] = fmaxf(mq[i & 3], (c + i < valid) ? v[i] : -INFINITY);
             }
-          }
+          };
+          tmem_ld32(s_addr, v0);
+          tmem_ld_wait();
+          tmem_ld32(s_addr + 32, v1);
+          take(0, v0);
+          tmem_ld_wait();
+          tmem_ld32(s_addr + 64, v0);
+          take(32, v1);
+          tmem_ld_wait();
+          tmem_ld32(s_addr + 96, v1);
+          take(64, v0);
+          tmem_ld_wait();
+          take(96, v1);
+          mx = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
         }
         const float m_new = fmaxf(m_run, mx * p.scale_log2);
         l *= fast_exp2(m_run - m_new);
@@ -308,30 +321,43 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // the previous product of this query tile is complete: fold it, and P may be overwritten
         if (j > 0) fold_o(j - 1, m_prev_tile);
         float lsum = 0.f;
+        {
+          float va[32], vb[32];
+          float lq[4] = {0.f, 0.f, 0.f, 0.f};       // independent partial sums (no 64-long dependent add chain)
+          auto emit = [&](int c, const float (&v)[32]) {
+            uint32_t w[16];
+            if (full) {
 #pragma unroll
-        for (int c = 0; c < ATT_BN; c += 32) {
-          float v[32];
-          tmem_ld32(s_addr + c, v);
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = fast_exp2(fmaf(v[i], p.scale_log2, -m_new));
+                const float p1 = fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new));
+                lq[(i >> 1) & 3] += p0 + p1;
+                w[i >> 1] = pack_bf16(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = (c + i < valid) ? fast_exp2(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
+                const float p1 = (c + i + 1 < valid) ? fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new)) : 0.f;
+                lq[(i >> 1) & 3] += p0 + p1;
+                w[i >> 1] = pack_bf16(p0, p1);
+              }
+            }
+            store_p(c, w);
+          };
+          tmem_ld32(s_addr, va);
           tmem_ld_wait();
-          uint32_t w[16];
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = fast_exp2(fmaf(v[i], p.scale_log2, -m_new));
-              const float p1 = fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new));
-              lsum += p0 + p1;
-              w[i >> 1] = pack_bf16(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = (c + i < valid) ? fast_exp2(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
-              const float p1 = (c + i + 1 < valid) ? fast_exp2(fmaf(v[i + 1], p.scale_log2, -m_new)) : 0.f;
-              lsum += p0 + p1;
-              w[i >> 1] = pack_bf16(p0, p1);
-            }
-          }
-          store_p(c, w);
+          tmem_ld32(s_addr + 32, vb);
+          emit(0, va);
+          tmem_ld_wait();
+          tmem_ld32(s_addr + 64, va);
+          emit(32, vb);
+          tmem_ld_wait();
+          tmem_ld32(s_addr + 96, vb);
+          emit(64, va);
+          tmem_ld_wait();
+          emit(96, vb);
+          lsum = (lq[0] + lq[1]) + (lq[2] + lq[3]);
         }
         l += lsum;
         fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
