@@ -127,15 +127,15 @@ def cpu_oracle_forward_seconds(res, crop=None, threads=None):
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU path (oracle port; the reference is pure Python
     on torch CPU ops, which is exactly what the oracle restates) on all host threads.  Each step is a
-    bounded sample: one fp32 U-Net forward of the full-width model on a 16 x (10 x 16) crop of the
-    latent (1/16 of the 40 x 64 pixels); per-pixel cost is extrapolated linearly to the full latent
+    bounded sample: one fp32 U-Net forward of the full-width model on a 16 x (24 x 32) crop of the
+    latent (3/10 of the 40 x 64 pixels); per-pixel cost is extrapolated linearly to the full latent
     (this favours the CPU: spatial attention grows quadratically) and doubled for the two CFG branches."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     from oracle import unet_oracle
-    sd, ucfg, x, t, ctx, fs, latent = cpu_oracle_forward_seconds("512", crop=(10, 16))
-    frac = (10 * 16) / (40 * 64)
+    sd, ucfg, x, t, ctx, fs, latent = cpu_oracle_forward_seconds("512", crop=(24, 32))
+    frac = (24 * 32) / (40 * 64)
     for _ in range(max(1, min(args.warmup, 2))):
         unet_oracle.unet_forward(sd, ucfg, x, t, ctx, fs)
     ts = []
@@ -151,8 +151,8 @@ def run_reference(args):
                 config=dict(workload="DynamiCrafter 320x512 16-frame CFG DDIM step (2 U-Net forwards), CPU fp32",
                             latent=[4, 16, 40, 64], context=[333, 1024]),
                 cpu_baseline=dict(value=v, unit="steps/s", cores=torch.get_num_threads(), kind="port",
-                                  sample="per step: 1 fp32 oracle forward, full-width U-Net, latent crop 16x10x16 "
-                                         "(1/16 of the pixels), scaled x16 x2 branches"),
+                                  sample="per step: 1 fp32 oracle forward, full-width U-Net, latent crop 16x24x32 "
+                                         "(3/10 of the pixels), scaled x10/3 x2 branches"),
                 e2e=dict(value=v, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -314,12 +314,20 @@ def main():
                      for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
         fam = [a for k, a in agg.items() if k.startswith("tc_gemm") or k.startswith("tc_conv")]
         pk = peaks()
+        # DRAM traffic of the family's most expensive launch shape, from the committed `ncu --set full` capture
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if args.res == "512" and os.path.exists(tpath):
+            t0 = json.load(open(tpath))["launches"][0]
+            traffic = t0["dram_bytes"]
+            traffic_note = dict(launch=t0["launch"], dram_bytes=t0["dram_bytes"], algorithmic_bytes=t0["algorithmic_bytes"],
+                                source="profiles/r1_ncu_full_key_metrics.md row 1 (ncu --set full, per launch)")
         if fam:
             fl, ms, n = sum(a["flops"] for a in fam), sum(a["ms"] for a in fam), sum(a["n"] for a in fam)
             ach = fl / ms / 1e9
             roofline = dict(bound="tensor", kernel="tc_gemm_kernel (Linear + conv3x3 + temporal conv, tcgen05)",
                             achieved=round(ach, 1), peak=pk["bf16"], unit="TFLOP/s", frac=round(ach / pk["bf16"], 4),
-                            traffic=None, launches_per_step=n, avg_launch_us=round(ms / n * 1e3, 2),
+                            traffic=traffic, traffic_of=traffic_note, launches_per_step=n, avg_launch_us=round(ms / n * 1e3, 2),
                             flops_per_launch=fl / n, share_of_step=round(ms / tot, 4), peak_source=pk["src"] + " sustained",
                             how="per-launch CUDA events on the launching stream, instrumented eager step after the timed region")
         whole = 2 * FLOP_PER_FORWARD[args.res] / (ms_step * 1e-3) / 1e12 / clip_ways     # per GPU

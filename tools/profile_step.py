@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--top", type=int, default=80)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--ncu", action="store_true", help="one warm-up forward + one forward, nothing else (for ncu)")
     a = ap.parse_args()
     latent = config.LATENT_512 if a.res == "512" else config.LATENT_1024
     with torch.device("cuda"):
@@ -31,9 +32,17 @@ def main():
     inp = {k: v.cuda() for k, v in synth_inputs(a.batch, latent, 1024, 0).items()}
     x = torch.cat([inp["x"], inp["c_concat"]], 1)
     t = torch.full((a.batch,), 499, device="cuda")
-    for _ in range(2):
+    for _ in range(1 if a.ncu else 2):
         m(x, t, context=inp["context"])
     torch.cuda.synchronize()
+    if a.ncu:                      # ncu --profile-from-start off: only the kernels of this forward are captured
+        l0 = abi.launches
+        torch.cuda.profiler.start()
+        m(x, t, context=inp["context"])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps(dict(event="forward_done", launches=abi.launches - l0)))
+        return
     abi.profile_begin()
     m(x, t, context=inp["context"])
     agg = {}
