@@ -39,15 +39,18 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
-constexpr int NUM_EPI_WARPS = 8;                        // two teams of four
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;    // 320
+// epilogue teams of four warps (a team covers the four TMEM lane quarters): two, or four for the GEGLU kernels whose
+// epilogue evaluates an erf per accumulator element (with K = 320 that, not the tensor pipe, set the pace)
+constexpr int MAX_TEAMS = 4;
+__host__ __device__ constexpr int num_teams(bool geglu) { return geglu ? 4 : 2; }
+__host__ __device__ constexpr int num_threads(bool geglu) { return 64 + 128 * num_teams(geglu); }     // 320 / 576
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_CHUNK = 32;                           // accumulator columns per epilogue chunk
 constexpr int EPI_SLOTS = 2;                            // staging slots per team
 constexpr int EPI_SLOT_F32 = BLOCK_M * EPI_CHUNK * 4;   // 16 KiB: [128][32] fp32, 128B-swizzled rows
 constexpr int EPI_SLOT_BF16 = BLOCK_M * EPI_CHUNK * 2;  //  8 KiB: [128][32] bf16,  64B-swizzled rows
-constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 4 + 2 * EPI_SLOTS) + 16;
+constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 4 + MAX_TEAMS * EPI_SLOTS) + 16;
 constexpr int SMEM_TOTAL = 227 * 1024;
 
 struct TcParams {
@@ -153,6 +156,7 @@ template <int MODE, bool GEGLU, typename TC, bool PAIR>
 __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUtensorMap* tmR, const TcParams& p,
                                               uint32_t tmem_base, uint32_t epi_base, uint32_t tfull0, uint32_t tempty0,
                                               uint32_t rfull0, int first, int step, int total, int rank, int q_pair) {
+  constexpr int NT = num_teams(GEGLU);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int team = (warp - 2) >> 2;
   const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
@@ -211,7 +215,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
     mbar_wait(tfull0 + 8u * acc, acc_phase);
     tc_fence_after();
     const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
-    for (int ci = team; ci < n_chunks; ci += 2) {
+    for (int ci = team; ci < n_chunks; ci += NT) {
       const int c0 = ci * EPI_CHUNK;
       const int cw = out_cols - c0 < EPI_CHUNK ? out_cols - c0 : EPI_CHUNK;   // 32, or 16 on a ragged last chunk
       const int slot = (int)(cnt % (uint32_t)n_slots);
@@ -245,7 +249,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
           for (int j = 0; j < 16; ++j) v[h + j] = 0.f;
         }
       }
-      if (ci + 2 >= n_chunks) {
+      if (ci + NT >= n_chunks) {
         // this team's last read of the accumulator buffer: hand it back to the MMA warp early
         tc_fence_before();
         __syncwarp();
@@ -316,7 +320,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
         tma_store_4d(tmC, sbuf, c[0], c[1], c[2], c[3]);
         bulk_commit();
         if (RES) {
-          int nwork = work, nci = ci + 2;
+          int nwork = work, nci = ci + NT;
           if (nci >= n_chunks) { nci = team; nwork += step; }
           if (nwork < total) {
             const int nslot = (int)((cnt + 1) % (uint32_t)n_slots);
@@ -344,7 +348,7 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
 }
 
 template <int MODE, bool GEGLU, typename TC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(GEGLU), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -352,15 +356,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_stage_bytes = p.block_n * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  const uint32_t epi_base = smem_base + p.stages * stage_bytes;          // 2 teams x EPI_SLOTS staging slots
-  const uint32_t bar_base = epi_base + 2 * p.epi_slots * p.slot_bytes;
+  const uint32_t epi_base = smem_base + p.stages * stage_bytes;          // teams x epi_slots staging slots
+  const uint32_t bar_base = epi_base + num_teams(GEGLU) * p.epi_slots * p.slot_bytes;
   // barriers: full[stages], empty[stages], tmem_full[2], tmem_empty[2], rfull[2*SLOTS]; then the TMEM base slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t rfull0 = bar_base + 8u * (2 * MAX_STAGES + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + 2 * EPI_SLOTS);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * EPI_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -372,8 +376,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmC);
     if (p.epi & PB_EPI_RESIDUAL) prefetch_tmap(&tmR);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), NUM_EPI_WARPS); }
-    for (int s = 0; s < 2 * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * num_teams(GEGLU)); }
+    for (int s = 0; s < MAX_TEAMS * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -538,7 +542,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 }
 
 template <int MODE, bool GEGLU, typename TC>
-__global__ void __launch_bounds__(NUM_THREADS, 1)      // cluster of 2 * p.mc CTAs (launch attribute)
+__global__ void __launch_bounds__(num_threads(GEGLU), 1)      // cluster of 2 * p.mc CTAs (launch attribute)
 tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -546,13 +550,13 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int half_n = p.block_n >> 1;                        // W rows staged by this CTA
   const int stage_bytes = A_STAGE_BYTES + half_n * BLOCK_K * 2;
   const uint32_t epi_base = smem_base + p.stages * stage_bytes;
-  const uint32_t bar_base = epi_base + 2 * p.epi_slots * p.slot_bytes;
+  const uint32_t bar_base = epi_base + num_teams(GEGLU) * p.epi_slots * p.slot_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // used in the leader only
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };       // one per CTA (multicast commit)
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };   // one per CTA (multicast commit)
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };  // leader only, 16 arrivals
   const uint32_t rfull0 = bar_base + 8u * (2 * MAX_STAGES + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + 2 * EPI_SLOTS);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * EPI_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -576,8 +580,8 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (p.epi & PB_EPI_RESIDUAL) prefetch_tmap(&tmR);
     // a stage is refilled by multicast from every pair of the cluster: all of them must have consumed it
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), (uint32_t)p.mc); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * NUM_EPI_WARPS); }
-    for (int s = 0; s < 2 * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * num_teams(GEGLU)); }
+    for (int s = 0; s < MAX_TEAMS * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -848,7 +852,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   int grid = p.m_tiles * p.n_tiles * p.splits;
   if (grid > num_sms()) grid = num_sms();
-  kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, tmC, tmR, p);
+  kern<<<grid, num_threads(GEGLU), smem, st>>>(tmA, tmB, tmC, tmR, p);
   PB_LAUNCH_CHECK("tc_gemm_kernel");
   return PB_OK;
 }
@@ -870,7 +874,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.blockDim = dim3(num_threads(GEGLU)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
   if (max_clusters[p.mc] == 0) {
     cfg.gridDim = dim3((unsigned)(num_sms() / csize * csize));
     int n = 0;
@@ -1145,7 +1149,7 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   if (slots_force == 1 || slots_force == 2) p.epi_slots = slots_force;
   static const int pf_force = []() { const char* e = getenv("PB_TC_PF"); return e ? atoi(e) : -1; }();
   p.pf_dist = pf_force >= 0 ? pf_force : 0;
-  const int epi_bytes = 2 * p.epi_slots * p.slot_bytes;
+  const int epi_bytes = num_teams(geglu) * p.epi_slots * p.slot_bytes;
   const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = (SMEM_TOTAL - 1024 - epi_bytes - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
