@@ -131,6 +131,14 @@ size_t pb_groupnorm_cols_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int32_t
 int pb_groupnorm_stats_cols(const float* colstats, int64_t ld_colstats, int64_t n_inst, int64_t rows_per_inst,
                             int64_t C, int32_t groups, float eps, const float* gamma, const float* beta,
                             float* scale_shift /* [n_inst, 2, C] */, void* ws, size_t ws_bytes, pb_stream_t stream);
+/* The hot-path form: GroupNorm(+SiLU) of x from the producer's column statistics in two launches (slab-range partial
+ * sums in fp64, then the apply pass, which folds the partials in its prologue: no finalize launch, no scale/shift
+ * buffer).  ws: pb_groupnorm_apply_cols_ws_bytes. */
+size_t pb_groupnorm_apply_cols_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int32_t groups);
+int pb_groupnorm_apply_cols(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,
+                            const float* colstats, int64_t ld_colstats, int64_t n_inst, int64_t rows_per_inst,
+                            int64_t C, int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
+                            void* ws, size_t ws_bytes, pb_stream_t stream);
 int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype,
                        int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
                        const float* scale_shift, int32_t silu, pb_stream_t stream);

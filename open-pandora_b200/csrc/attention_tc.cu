@@ -24,14 +24,14 @@ namespace pb {
 namespace tc {
 
 constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64;
-constexpr int KV_STAGES = 3;
-constexpr int ATT_QT = 2;                       // query tiles per CTA
-constexpr int ATT_THREADS = 64 + 128 * ATT_QT;  // 320
+// Two instantiations: <QT=2, ST=3> (two query tiles per CTA in ping-pong, 3-stage K/V ring, 512 TMEM columns, one CTA
+// per SM) for self-attention, and <QT=1, ST=1> (80 KB of shared memory, 256 TMEM columns -> two CTAs per SM) for
+// launches with a single key tile (cross-attention: per-CTA latency, not throughput, is what matters there)
 constexpr int UMMA_K = 16;
 constexpr int TILE_BYTES = 128 * 64 * 2;      // 16 KiB: one [128 x 64] bf16 tile
 constexpr int P_BYTES = 2 * TILE_BYTES;       // [128 x 128] bf16 as two K-blocks
-constexpr int ATT_SMEM = TILE_BYTES * (ATT_QT + 2 * KV_STAGES) + ATT_QT * P_BYTES;   // 192 KiB
-constexpr int S_COL0 = 0, O_COL0 = 256;       // TMEM columns: S of query tile t at t*128, O at 256 + t*64
+__host__ __device__ constexpr int att_smem(int QT, int ST) { return TILE_BYTES * (QT + 2 * ST) + QT * P_BYTES; }   // 192 / 80 KiB
+constexpr int S_COL0 = 0;                     // TMEM columns: S of query tile t at t*128, O at QT*128 + t*64
 
 struct AttP {
   void* out;
@@ -88,7 +88,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int ATT_QT, int KV_STAGES, int TMEM_NCOLS>
+__global__ void __launch_bounds__(64 + 128 * ATT_QT, ATT_QT == 1 ? 2 : 1)
 tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttP p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -97,6 +98,8 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   auto sK = [&](int s) { return base + TILE_BYTES * (ATT_QT + s); };
   auto sV = [&](int s) { return base + TILE_BYTES * (ATT_QT + KV_STAGES + s); };
   auto sP = [&](int t) { return base + TILE_BYTES * (ATT_QT + 2 * KV_STAGES) + P_BYTES * t; };
+  constexpr int ATT_SMEM = att_smem(ATT_QT, KV_STAGES);
+  constexpr int O_COL0 = ATT_QT * ATT_BN;
   const uint32_t bars = base + ATT_SMEM;
   const uint32_t q_full = bars;
   auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
@@ -118,7 +121,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, TMEM_NCOLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -157,7 +160,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       };
       mbar_wait(q_full, 0);
       issue_s(0, 0);
-      issue_s(1, 0);
+      if (ATT_QT > 1) issue_s(1, 0);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % KV_STAGES;
 #pragma unroll
@@ -395,7 +398,7 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_NCOLS);
 }
 
 static int encode_rows3d(CUtensorMap* m, const pb_attn_operand& o, int64_t cols, int64_t rows, int64_t n_batch) {
@@ -447,17 +450,26 @@ extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
   p.accumulate = a->accumulate;
   p.split = a->kv_split;
 
-  static bool configured = false;
-  const size_t smem = ATT_SMEM + 1024 + 8 * (8 + 2 * KV_STAGES) + 16;
   if (a->kv_split < 0 || (a->kv_split > 0 && (a->n_kv > ATT_BN || a->kv_split >= a->n_kv)))
     ATT_UNSUPPORTED("pb_tc_attention: kv_split needs 0 < kv_split < n_kv <= 128");
+  static bool configured = false;
+  auto k_self = tc_attention_kernel<2, 3, 512>;
+  auto k_one = tc_attention_kernel<1, 1, 256>;
+  const size_t smem_self = att_smem(2, 3) + 1024 + 8 * (8 + 2 * 3) + 16;
+  const size_t smem_one = att_smem(1, 1) + 1024 + 8 * (8 + 2 * 1) + 16;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_self, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_self);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_one);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attention_kernel)");
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM * ATT_QT), (unsigned)a->heads, (unsigned)a->batch);
-  tc_attention_kernel<<<grid, ATT_THREADS, smem, to_stream(stream)>>>(tq, tk, tv, p);
+  if (p.kv_tiles == 1) {
+    dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM), (unsigned)a->heads, (unsigned)a->batch);
+    k_one<<<grid, 192, smem_one, to_stream(stream)>>>(tq, tk, tv, p);
+  } else {
+    dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM * 2), (unsigned)a->heads, (unsigned)a->batch);
+    k_self<<<grid, 320, smem_self, to_stream(stream)>>>(tq, tk, tv, p);
+  }
   PB_LAUNCH_CHECK("tc_attention_kernel");
   return PB_OK;
 #undef ATT_UNSUPPORTED

@@ -9,6 +9,8 @@
 //           per-channel (scale, shift).
 //   Pass 3  gn_apply_kernel   : y = x*scale + shift (+SiLU), vectorised, no integer division in the loop,
 //           written in the operand dtype the next GEMM wants (bf16 or fp32).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace pb {
@@ -305,12 +307,38 @@ __global__ void gn_affine_kernel(const double* __restrict__ sums, int C, int G, 
   scale_shift[(int64_t)inst * 2 * C + C + c] = beta[c] - (float)mean * a;
 }
 
+// Folded-finalize variant (part != nullptr): the per-(instance, group) fp64 partial sums of gn_cols_partial_kernel are
+// folded by every CTA in its prologue (G threads x `splits` loads), so no separate finalize launch and no
+// scale/shift buffer exist; the affine is built in registers from gamma / beta.
+struct GnFold {
+  const double* part;     // [(inst * G + g) * splits + sp][2]
+  const float* gamma;
+  const float* beta;
+  int splits, G;
+  double count;           // elements per (instance, group)
+  float eps;
+};
+
 template <typename TX_, typename TY_>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int64_t R, int C,
-                const float* __restrict__ scale_shift, int silu, int TX, int TY, int rows_per_cta) {
+                const float* __restrict__ scale_shift, int silu, int TX, int TY, int rows_per_cta, GnFold fold) {
+  __shared__ float g_mean[32], g_rstd[32];
   const int inst = blockIdx.y;
   const int cv = C >> 2;
+  if (fold.part != nullptr) {
+    if (threadIdx.x < fold.G) {
+      const double* pp = fold.part + ((int64_t)inst * fold.G + threadIdx.x) * fold.splits * 2;
+      double ss = 0.0, qq = 0.0;
+      for (int i = 0; i < fold.splits; ++i) { ss += pp[2 * i]; qq += pp[2 * i + 1]; }
+      const double mean = ss / fold.count;
+      double var = qq / fold.count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      g_mean[threadIdx.x] = (float)mean;
+      g_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)fold.eps));
+    }
+    __syncthreads();
+  }
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   if (ty >= TY) return;
   const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
@@ -320,8 +348,18 @@ gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int
   TY_* yb = y + (int64_t)inst * R * ldy;
   for (int v = tx; v < cv; v += TX) {
     float a[4], b[4];
-    load4(sc + v * 4, a);
-    load4(sc + C + v * 4, b);
+    if (fold.part != nullptr) {
+      const int cpg = C / fold.G;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = v * 4 + j, g = c / cpg;
+        a[j] = g_rstd[g] * fold.gamma[c];
+        b[j] = fold.beta[c] - g_mean[g] * a[j];
+      }
+    } else {
+      load4(sc + v * 4, a);
+      load4(sc + C + v * 4, b);
+    }
     int64_t r = r_begin + ty;
     for (; r + 3 * TY < r_end; r += 4 * TY) {         // 4 independent 16-byte loads in flight per thread
       float t[4][4];
@@ -422,6 +460,48 @@ int pb_groupnorm_stats_cols(const float* colstats, int64_t ld_colstats, int64_t 
   return PB_OK;
 }
 
+int pb_groupnorm_apply_cols(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,
+                            const float* colstats, int64_t ld_colstats, int64_t n_inst, int64_t rows_per_inst,
+                            int64_t C, int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
+                            void* ws, size_t ws_bytes, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(x && y && colstats && gamma && beta && ws, "pb_groupnorm_apply_cols: null pointer");
+  PB_REQUIRE(n_inst > 0 && n_inst <= 65535 && rows_per_inst > 0 && C > 0 && groups > 0 && groups <= 32 &&
+                 C % groups == 0, "pb_groupnorm_apply_cols: bad sizes");
+  PB_REQUIRE(rows_per_inst % 32 == 0, "pb_groupnorm_apply_cols: rows_per_inst must be a multiple of 32 (the slab)");
+  PB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "pb_groupnorm_apply_cols: need C %% 4 == 0, ld %% 4 == 0");
+  PB_REQUIRE(ld_colstats >= 2 * C && ld_colstats % 2 == 0, "pb_groupnorm_apply_cols: bad ld_colstats");
+  const int splits = gn_cols_splits(n_inst, rows_per_inst, groups);
+  PB_REQUIRE(ws_bytes >= (size_t)n_inst * groups * splits * 2 * sizeof(double),
+             "pb_groupnorm_apply_cols: workspace too small");
+  cudaStream_t st = to_stream(stream);
+  dim3 pgrid((unsigned)(n_inst * groups), (unsigned)splits);
+  gn_cols_partial_kernel<<<pgrid, 256, 0, st>>>(colstats, ld_colstats, (int)C, groups, rows_per_inst, splits,
+                                                reinterpret_cast<double*>(ws));
+  PB_LAUNCH_CHECK("gn_cols_partial_kernel");
+  int TX, TY;
+  gn_shape((int)(C / 4), &TX, &TY);
+  const int rows_per_cta = 8 * TY;
+  dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
+  GnFold fold;
+  fold.part = reinterpret_cast<const double*>(ws); fold.gamma = gamma; fold.beta = beta;
+  fold.splits = splits; fold.G = groups; fold.count = (double)rows_per_inst * (double)(C / groups); fold.eps = eps;
+  PB_DISPATCH_DTYPE(x_dtype, TXT, {
+    PB_DISPATCH_DTYPE(y_dtype, TYT, {
+      gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const TXT*>(x), ldx,
+                                                             reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
+                                                             nullptr, silu, TX, TY, rows_per_cta, fold);
+    })
+  })
+  PB_LAUNCH_CHECK("gn_apply_kernel");
+  return PB_OK;
+}
+
+size_t pb_groupnorm_apply_cols_ws_bytes(int64_t n_inst, int64_t rows_per_inst, int32_t groups) {
+  if (n_inst <= 0 || rows_per_inst <= 0 || groups <= 0) return 0;
+  return (size_t)n_inst * groups * pb::gn_cols_splits(n_inst, rows_per_inst, groups) * 2 * sizeof(double);
+}
+
 int pb_groupnorm_sums(const void* x, int32_t x_dtype, int64_t ldx, int64_t n_inst, int64_t rows_per_inst,
                       int64_t C, int32_t groups, double* sums, void* ws, size_t ws_bytes, pb_stream_t stream) {
   using namespace pb;
@@ -471,9 +551,11 @@ int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int
   dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
   PB_DISPATCH_DTYPE(x_dtype, TXT, {
     PB_DISPATCH_DTYPE(y_dtype, TYT, {
+      GnFold nofold;
+      memset(&nofold, 0, sizeof(nofold));
       gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const TXT*>(x), ldx,
                                                              reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
-                                                             scale_shift, silu, TX, TY, rows_per_cta);
+                                                             scale_shift, silu, TX, TY, rows_per_cta, nofold);
     })
   })
   PB_LAUNCH_CHECK("gn_apply_kernel");

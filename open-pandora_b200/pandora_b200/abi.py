@@ -62,6 +62,9 @@ SYMBOLS = {
     "pb_tc_gemm_workspace_bytes": (_sz, [C.POINTER(GemmArgs)]),
     "pb_tc_gemm_colstats_ok": (C.c_int, [C.POINTER(GemmArgs)]),
     "pb_groupnorm_cols_ws_bytes": (_sz, [_i64, _i64, _i32]),
+    "pb_groupnorm_apply_cols_ws_bytes": (_sz, [_i64, _i64, _i32]),
+    "pb_groupnorm_apply_cols": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp,
+                                          _i32, _vp, _sz, _vp]),
     "pb_groupnorm_stats_cols": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pb_groupnorm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "pb_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -258,15 +261,16 @@ def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32, co
     st = _stream()
     if colstats is not None:
         assert rows_per_inst % 32 == 0 and colstats.shape[0] * 32 == x.shape[0] and colstats.shape[1] == 2 * Cc
-        stats = torch.empty(n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
         cp, ldcs = _rows(colstats)
         tok = _tick("groupnorm_fused", 0, _nbytes(x) + _nbytes(y), f"inst{n_inst} rows{rows_per_inst} C{Cc}")
-        wsb = lib.pb_groupnorm_cols_ws_bytes(n_inst, rows_per_inst, groups)
-        ws = torch.empty(wsb // 8, dtype=torch.float64, device=x.device) if wsb else None
-        _check(lib.pb_groupnorm_stats_cols(cp, ldcs, n_inst, rows_per_inst, Cc, groups, eps, gamma.data_ptr(),
-                                           beta.data_ptr(), stats.data_ptr(), _ptr(ws), wsb, st),
-               "pb_groupnorm_stats_cols")
-        launches += 3 if wsb else 2
+        wsb = lib.pb_groupnorm_apply_cols_ws_bytes(n_inst, rows_per_inst, groups)
+        ws = torch.empty(wsb // 8, dtype=torch.float64, device=x.device)
+        _check(lib.pb_groupnorm_apply_cols(xp, dt(x), ldx, yp, dt(y), ldy, cp, ldcs, n_inst, rows_per_inst, Cc, groups,
+                                           eps, gamma.data_ptr(), beta.data_ptr(), int(silu), ws.data_ptr(), wsb, st),
+               "pb_groupnorm_apply_cols")
+        _tock(tok)
+        launches += 2
+        return None
     else:
         ws_bytes = lib.pb_groupnorm_ws_bytes(n_inst, rows_per_inst, Cc)
         ws = torch.empty(ws_bytes // 4 + n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
