@@ -170,6 +170,9 @@ def main():
     ap.add_argument("--cfg-par", type=int, default=1, choices=[1, 2],
                     help="2 = the cond / uncond branches of a step on two ranks (one all-gather of v per step)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--torch-baseline", action="store_true",
+                    help="also time the reference's op sequence (the oracle: stock torch ops -> cuDNN / cuBLAS / einsum "
+                         "attention, bf16) on this GPU and report it as torch_gpu_baseline (informational)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if os.environ.get("PB_BENCH_WATCHDOG"):       # debugging aid: dump every thread's stack and exit after N seconds
@@ -341,6 +344,32 @@ def main():
         cpu_baseline = dict(value=1.0 / (2 * sec), unit="steps/s", cores=torch.get_num_threads(), kind="port",
                             sample=f"1 fp32 oracle U-Net forward at the full latent ({sec:.1f} s, no warm-up); "
                                    "a CFG step = 2 forwards")
+    torch_gpu = None
+    if rank == 0 and world == 1 and args.torch_baseline:
+        # what the unmodified reference does on this box: the same op sequence through stock PyTorch kernels
+        from oracle import unet_oracle
+        from pandora_b200 import config as _cfg
+        from pandora_b200.synthetic import synth_state_dict
+        del g
+        torch.cuda.empty_cache()
+        ocfg = _cfg.UNET_512
+        sd = {k: v.to(dev, torch.bfloat16) for k, v in synth_state_dict(unet_oracle.unet_param_shapes(ocfg), 1234).items()}
+        xo = torch.cat([d["x"], d["c_concat"]], 1).to(torch.bfloat16)
+        to = torch.tensor([999], device=dev)
+        ts_ms = []
+        with torch.no_grad():
+            for i in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                unet_oracle.unet_forward(sd, ocfg, xo, to, d["context"].to(torch.bfloat16), fs)
+                e1.record()
+                e1.synchronize()
+                ts_ms.append(e0.elapsed_time(e1))
+        fwd = min(ts_ms[1:])
+        torch_gpu = dict(ms_per_forward=round(fwd, 2), steps_per_s=round(1e3 / (2 * fwd), 3),
+                         note="oracle (the reference's op sequence as stock torch ops: cuDNN conv, cuBLAS GEMM, einsum "
+                              "attention with a materialised score matrix), bf16, eager, one forward = half a CFG step")
+        del sd
     if rank == 0:
         line = dict(metric=METRIC if args.res == "512" else METRIC.replace("320x512", "576x1024"), value=value, unit="steps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak" if clip_ways == 1 else "strong",
@@ -359,6 +388,8 @@ def main():
                     gpu_launches=launches, clocks=clk, roofline=roofline, cpu_baseline=cpu_baseline,
                     whole_step_tflops=round(whole, 1), whole_step_frac_of_peak=round(whole / peaks()["bf16"], 4),
                     sec_per_50_step_clip=round(S_DDIM * ms_step * 1e-3, 3), breakdown=breakdown)
+        if torch_gpu is not None:
+            line["torch_gpu_baseline"] = torch_gpu
         print(json.dumps(line), flush=True)
     if world > 1:
         if clip_ways > 1:

@@ -42,6 +42,10 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--simt", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--torch", action="store_true",
+                    help="also time the kernels the reference's torch ops dispatch to on this box (cuDNN conv2d / conv3d "
+                         "channels-last bf16, F.scaled_dot_product_attention as the xformers stand-in, einsum attention, "
+                         "F.group_norm + F.silu) on the same shapes: the `torch_*` rows")
     a = ap.parse_args()
     H, W = (40, 64) if a.res == "512" else (72, 128)
     dev = "cuda"
@@ -104,6 +108,70 @@ def main():
                 rows.append(dict(kind="groupnorm_" + tag, C=C, rows=16 * hw, ms=t * 1e3, gbs=(2 * x.numel() * 4 + y.numel() * 2) / t / 1e9))
             t = timeit(lambda: abi.layernorm(x, y, gmm, bt), a.reps, flush)
             rows.append(dict(kind="layernorm", C=C, rows=16 * hw, ms=t * 1e3, gbs=(x.numel() * 4 + y.numel() * 2) / t / 1e9))
+    if a.torch:
+        import torch.nn.functional as F
+        torch.backends.cudnn.benchmark = True
+        with torch.no_grad():
+            if "conv" in what:
+                for i, (cin, cout) in enumerate([(320, 320), (640, 640), (1280, 1280), (1280, 1280)]):
+                    h, w_ = H >> i, W >> i
+                    x = rn(16, cin, h, w_).contiguous(memory_format=torch.channels_last)
+                    w = rn(cout, cin, 3, 3).contiguous(memory_format=torch.channels_last)
+                    bias = rn(cout)
+                    t = timeit(lambda: F.conv2d(x, w, bias, padding=1), a.reps, flush)
+                    rows.append(dict(kind="torch_conv3x3_cudnn", cin=cin, cout=cout, H=h, W=w_, ms=t * 1e3,
+                                     tflops=2 * 16 * h * w_ * cout * 9 * cin / t / 1e12))
+            if "convt" in what:
+                for i, C in enumerate([320, 640, 1280, 1280]):
+                    h, w_ = H >> i, W >> i
+                    x = rn(1, C, 16, h, w_).contiguous(memory_format=torch.channels_last_3d)
+                    w = rn(C, C, 3, 1, 1).contiguous(memory_format=torch.channels_last_3d)
+                    bias = rn(C)
+                    t = timeit(lambda: F.conv3d(x, w, bias, padding=(1, 0, 0)), a.reps, flush)
+                    rows.append(dict(kind="torch_convt3_cudnn", C=C, HW=h * w_, ms=t * 1e3,
+                                     tflops=2 * 16 * h * w_ * C * 3 * C / t / 1e12))
+            if "attn" in what:
+                for i, C in enumerate([320, 640, 1280]):
+                    n, heads = (H >> i) * (W >> i), C // 64
+                    q, k, v = (rn(16, heads, n, 64) for _ in range(3))
+                    t = timeit(lambda: F.scaled_dot_product_attention(q, k, v), a.reps, flush)
+                    rows.append(dict(kind="torch_attn_self_sdpa", n=n, heads=heads, ms=t * 1e3,
+                                     tflops=4 * 16 * heads * n * n * 64 / t / 1e12))
+
+                    def einsum_attn():      # the path the reference takes without xformers (attention.py:101-125)
+                        sim = torch.einsum("bhid,bhjd->bhij", q, k) * 0.125
+                        return torch.einsum("bhij,bhjd->bhid", sim.softmax(dim=-1), v)
+                    t = timeit(einsum_attn, a.reps, flush)
+                    rows.append(dict(kind="torch_attn_self_einsum", n=n, heads=heads, ms=t * 1e3,
+                                     tflops=4 * 16 * heads * n * n * 64 / t / 1e12))
+                for C, hw in ((320, H * W), (640, H * W // 4), (1280, H * W // 16)):
+                    heads = C // 64
+                    q, k, v = (rn(hw, heads, 16, 64) for _ in range(3))       # temporal: batch = pixels, seq 16
+                    t = timeit(lambda: F.scaled_dot_product_attention(q, k, v), a.reps, flush)
+                    rows.append(dict(kind="torch_attn_temporal_sdpa", pixels=hw, heads=heads, ms=t * 1e3,
+                                     gbs=4 * hw * 16 * C * 2 / t / 1e9))
+            if "norm" in what:
+                for i, C in enumerate([320, 640, 1280, 1280]):
+                    h, w_ = H >> i, W >> i
+                    x = rn(16, C, h, w_).contiguous(memory_format=torch.channels_last)
+                    gmm, bt = torch.ones(C, device=dev, dtype=BF), torch.zeros(C, device=dev, dtype=BF)
+                    t = timeit(lambda: F.silu(F.group_norm(x, 32, gmm, bt, 1e-5)), a.reps, flush)
+                    rows.append(dict(kind="torch_groupnorm_silu", C=C, rows=16 * h * w_, ms=t * 1e3,
+                                     gbs=(4 * x.numel() * 2) / t / 1e9))
+                    xr = rn(16 * h * w_, C)
+                    t = timeit(lambda: F.layer_norm(xr, (C,), gmm, bt), a.reps, flush)
+                    rows.append(dict(kind="torch_layernorm", C=C, rows=16 * h * w_, ms=t * 1e3,
+                                     gbs=(2 * xr.numel() * 2) / t / 1e9))
+    if "tattn" in what or "attn" in what:
+        for C, hw in ((320, H * W), (640, H * W // 4), (1280, H * W // 16)):
+            heads, T = C // 64, 16
+            qkv = rn(T * hw, 3 * C)
+            out = torch.empty(T * hw, C, device=dev, dtype=BF)
+            ld = 3 * C
+            op = lambda off: abi.operand(qkv, hw, T * hw * ld, ld, hw * ld, off)
+            t = timeit(lambda: abi.attention(op(0), op(C), op(2 * C), out, (hw, T * hw * C, C, hw * C), hw, heads, T, T,
+                                             0.125, abi.BF16), a.reps, flush)
+            rows.append(dict(kind="attn_temporal", pixels=hw, heads=heads, ms=t * 1e3, gbs=4 * hw * 16 * C * 2 / t / 1e9))
     for r in rows:
         print(json.dumps({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()}))
     if a.out:
