@@ -16,6 +16,7 @@
 // kv_split > 0 (n_kv <= 128): keys [0, split) and [split, n_kv) are two independent softmaxes whose outputs are
 // summed — text + image cross-attention (attention.py:128-142) in one pass over one concatenated K/V tile.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -401,6 +402,266 @@ tc_attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_NCOLS);
 }
 
+// ================================================================================================
+// Version 2 of the self-attention kernel (multi-tile K/V): the FlashAttention-4 data flow.
+//   * S_t,j is read from tensor memory ONCE into registers (128 fp32 per thread);
+//   * P_t,j goes back into tensor memory (bf16, aliasing the first 64 columns of S_t) with tcgen05.st and is the
+//     A operand of the PV product straight from TMEM (no shared-memory round trip, no proxy fence);
+//   * O_t accumulates in tensor memory across key tiles (the PV UMMAs accumulate); it is rescaled only when a row
+//     maximum grows by more than 2^8 (lazy rescale, decided per warp), otherwise the stale maximum is kept — the
+//     probabilities then stay below 2^8, exact in fp32 and harmless in bf16 — so the per-tile fold of O disappears.
+// Tensor-pipe ordering does the rest: S_t,j+1 is issued after PV_t,j by the same thread, so P_t,j is consumed before
+// the next S overwrites it, and PV_t,j-1 has completed before S_t,j (hence before the softmax of tile j starts).
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32f(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+      "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]),
+      "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]),
+      "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+
+constexpr int V2_STAGES = 4;
+constexpr int V2_SMEM = TILE_BYTES * (2 + 2 * V2_STAGES);      // Q x2 + (K, V) x4 = 160 KiB
+constexpr float V2_RESCALE_THRESHOLD = 8.0f;                    // log2 units
+
+// 384 threads = three warpgroups: {TMA producer, MMA issuer, two idle warps} | softmax of query tile 0 | softmax of
+// query tile 1.  setmaxnreg moves registers from the first warpgroup (88 each) to the softmax groups (208 each), so a
+// thread can hold its whole 128-wide score row.
+__global__ void __launch_bounds__(384, 1)
+tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttP p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto sQ = [&](int t) { return base + TILE_BYTES * t; };
+  auto sK = [&](int s) { return base + TILE_BYTES * (2 + s); };
+  auto sV = [&](int s) { return base + TILE_BYTES * (2 + V2_STAGES + s); };
+  const uint32_t bars = base + V2_SMEM;
+  const uint32_t q_full = bars;
+  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (1 + V2_STAGES + s); };
+  auto s_full = [&](int t) { return bars + 8u * (1 + 2 * V2_STAGES + t); };
+  auto p_full = [&](int t) { return bars + 8u * (3 + 2 * V2_STAGES + t); };
+  auto o_full = [&](int t) { return bars + 8u * (5 + 2 * V2_STAGES + t); };
+  const uint32_t tmem_slot = bars + 8u * (7 + 2 * V2_STAGES);
+  constexpr int O_COL0 = 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tile0 = blockIdx.x * 2, head = blockIdx.y, n = blockIdx.z;
+  const int n_tiles = p.kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < V2_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(s_full(t), 1); mbar_init(p_full(t), 128); mbar_init(o_full(t), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * TILE_BYTES);
+      for (int t = 0; t < 2; ++t)
+        tma_load_3d(sQ(t), &tmQ, q_full, head * ATT_D, (q_tile0 + t) * ATT_BM, n / p.q_bdiv);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % V2_STAGES;
+        mbar_wait(kv_empty(s), ((j / V2_STAGES) & 1) ^ 1);
+        mbar_expect_tx(kv_full(s), 2 * TILE_BYTES);
+        tma_load_3d(sK(s), &tmK, kv_full(s), head * ATT_D, j * ATT_BN, n / p.k_bdiv);
+        tma_load_3d(sV(s), &tmV, kv_full(s), head * ATT_D, j * ATT_BN, n / p.v_bdiv);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN);
+      const uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);     // B (= V) MN-major
+      auto issue_s = [&](int t, int j) {
+        const int s = j % V2_STAGES;
+        mbar_wait(kv_full(s), (j / V2_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t q_desc = make_smem_desc_sw128(sQ(t));
+        const uint64_t k_desc = make_smem_desc_sw128(sK(s));
+        const uint32_t d = tmem_base + (uint32_t)t * ATT_BN;
+#pragma unroll
+        for (int k = 0; k < ATT_D / UMMA_K; ++k) umma_bf16(d, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full(t));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % V2_STAGES;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(p_full(t), j & 1);         // P_t,j is in tensor memory, O_t has been rescaled if it had to be
+          tc_fence_after();
+          const uint32_t d = tmem_base + O_COL0 + (uint32_t)t * ATT_D;
+          const uint32_t a_tm = tmem_base + (uint32_t)t * ATT_BN;      // P aliases the head of S_t: 8 columns per k-step
+#pragma unroll
+          for (int k = 0; k < ATT_BN / UMMA_K; ++k) {
+            const uint64_t b_desc = make_smem_desc_mn_sw128(sV(s) + k * 16 * 128);
+            umma_bf16_ts(d, a_tm + (uint32_t)(k * 8), b_desc, idesc_o, (j | k) != 0);
+          }
+          umma_commit(o_full(t));
+          if (t == 1) umma_commit(kv_empty(s));
+          if (j + 1 < n_tiles) issue_s(t, j + 1);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int t = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t s_addr = lane_addr + (uint32_t)t * ATT_BN;
+    const uint32_t o_addr = lane_addr + O_COL0 + (uint32_t)t * ATT_D;
+    float m_run = -INFINITY, l = 0.f;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int valid = p.nkv - j * ATT_BN;
+      const bool full = valid >= ATT_BN;
+      mbar_wait(s_full(t), j & 1);
+      tc_fence_after();
+      // keys 0..63 stay in registers; keys 64..127 are read again for the exponentials (the register file of a
+      // 384-thread CTA holds 168 per thread; P only overwrites columns 0..63 of S, so the second half stays intact)
+      float v[2][32];
+      float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      auto take = [&](int c, const float (&x)[32]) {
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mq[i & 3] = fmaxf(mq[i & 3], x[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mq[i & 3] = fmaxf(mq[i & 3], (c + i < valid) ? x[i] : -INFINITY);
+        }
+      };
+      {
+        float u[32];
+        tmem_ld32(s_addr + 64, u);
+        tmem_ld32(s_addr, v[0]);
+        tmem_ld_wait();
+        take(64, u);
+        tmem_ld32(s_addr + 96, u);
+        tmem_ld32(s_addr + 32, v[1]);
+        take(0, v[0]);
+        tmem_ld_wait();
+        take(96, u);
+        take(32, v[1]);
+      }
+      const float m_tile = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3])) * p.scale_log2;
+      if (j == 0) {
+        m_run = m_tile;
+      } else {
+        const bool need = m_tile > m_run + V2_RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {        // warp-uniform: tcgen05.ld / st are warp-collective
+          mbar_wait(o_full(t), (j - 1) & 1);        // PV_t,j-1 is complete (it precedes S_t,j in the pipe)
+          tc_fence_after();
+          const float corr = need ? fast_exp2(m_run - m_tile) : 1.0f;
+          if (need) { m_run = m_tile; l *= corr; }
+#pragma unroll 1
+          for (int c = 0; c < ATT_D; c += 32) {      // 32 columns at a time: the score row is live in registers
+            float o0[32];
+            tmem_ld32(o_addr + c, o0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o0[i] *= corr;
+            tmem_st32f(o_addr + c, o0);
+          }
+        }
+      }
+      float lq[4] = {0.f, 0.f, 0.f, 0.f};
+      auto emit = [&](int c, const float (&x)[32]) {
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = fast_exp2(fmaf(x[i], p.scale_log2, -m_run));
+          float p1 = fast_exp2(fmaf(x[i + 1], p.scale_log2, -m_run));
+          if (!full) {
+            p0 = (c + i < valid) ? p0 : 0.f;
+            p1 = (c + i + 1 < valid) ? p1 : 0.f;
+          }
+          lq[(i >> 1) & 3] += p0 + p1;
+          w[i >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st16(s_addr + (uint32_t)(c >> 1), w);       // 32 keys = 16 packed columns
+      };
+      {
+        float u[32];
+        tmem_ld32(s_addr + 64, u);        // in flight while the first half is exponentiated
+        emit(0, v[0]);
+        emit(32, v[1]);
+        tmem_ld_wait();
+        float u2[32];
+        tmem_ld32(s_addr + 96, u2);
+        emit(64, u);
+        tmem_ld_wait();
+        emit(96, u2);
+      }
+      l += (lq[0] + lq[1]) + (lq[2] + lq[3]);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full(t));
+    }
+    // ---- epilogue: O_t / l
+    mbar_wait(o_full(t), (n_tiles - 1) & 1);
+    tc_fence_after();
+    const int64_t qi = (int64_t)(q_tile0 + t) * ATT_BM + r;
+    float o0[32], o1[32];
+    tmem_ld32(o_addr, o0);
+    tmem_ld32(o_addr + 32, o1);
+    tmem_ld_wait();
+    if (qi < p.nq) {
+      const float inv = 1.0f / l;
+      bf16* O = reinterpret_cast<bf16*>(p.out) + (n / p.o_bdiv) * p.o_bso + (n % p.o_bdiv) * p.o_bsi + qi * p.o_rs +
+                head * ATT_D;
+#pragma unroll
+      for (int c = 0; c < ATT_D; c += 8) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (c < 32 ? o0[c + i] : o1[c - 32 + i]) * inv;
+        uint4* dst = reinterpret_cast<uint4*>(O + c);
+        if (p.accumulate) {
+          uint4 prev = *dst;
+          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { o[2 * i] += __low2float(pv[i]); o[2 * i + 1] += __high2float(pv[i]); }
+        }
+        uint4 val;
+        val.x = pack_bf16(o[0], o[1]); val.y = pack_bf16(o[2], o[3]);
+        val.z = pack_bf16(o[4], o[5]); val.w = pack_bf16(o[6], o[7]);
+        *dst = val;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 static int encode_rows3d(CUtensorMap* m, const pb_attn_operand& o, int64_t cols, int64_t rows, int64_t n_batch) {
   uint64_t dims[3] = {(uint64_t)cols, (uint64_t)rows, (uint64_t)(n_batch < 1 ? 1 : n_batch)};
   uint64_t bs = o.bs_outer > 0 ? (uint64_t)o.bs_outer : (uint64_t)rows * o.rs;
@@ -463,9 +724,20 @@ extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attention_kernel)");
     configured = true;
   }
+  static const bool v2_on = []() { const char* e = getenv("PB_ATT_V2"); return !(e && e[0] == '0'); }();
+  static bool v2_configured = false;
+  const size_t smem_v2 = V2_SMEM + 1024 + 8 * (8 + 2 * V2_STAGES) + 16;
+  if (v2_on && !v2_configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attention2_kernel)");
+    v2_configured = true;
+  }
   if (p.kv_tiles == 1) {
     dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM), (unsigned)a->heads, (unsigned)a->batch);
     k_one<<<grid, 192, smem_one, to_stream(stream)>>>(tq, tk, tv, p);
+  } else if (v2_on) {
+    dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM * 2), (unsigned)a->heads, (unsigned)a->batch);
+    tc_attention2_kernel<<<grid, 384, smem_v2, to_stream(stream)>>>(tq, tk, tv, p);
   } else {
     dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM * 2), (unsigned)a->heads, (unsigned)a->batch);
     k_self<<<grid, 320, smem_self, to_stream(stream)>>>(tq, tk, tv, p);
