@@ -152,3 +152,41 @@ def test_sampler_bf16_psnr_vs_fp32_reference(name):
     # BASELINE.json's >= 40 dB is stated for the 50-step run; the short schedules leave no steps to average the
     # per-step rounding out (CFG 7.5 amplifies it ~8x), so they only get a sanity bound here
     assert q >= (PSNR_MIN if meta["S"] >= 50 else 35.0)
+
+
+def test_rollout_chains_rounds_like_pandora():
+    """BASELINE config 4 in miniature: 3 rounds, c_concat of round r+1 = last 4 frames of round r tiled (f0 f1 f2 f3
+    f0 ...), fresh context per round; the chained run equals running each round by hand."""
+    from pandora_b200 import DDIMSampler, LatentDiffusionLite, UNetModel, config
+    from pandora_b200.rollout import chain_c_concat, first_round_c_concat, rollout
+    from pandora_b200.synthetic import randomize_module_, synth_inputs
+    p = config.small_unet()
+    m = randomize_module_(UNetModel(**p).eval(), 9).cuda()
+    model = LatentDiffusionLite(m, **config.DIFFUSION_512).cuda()
+    shape = (4, 16, 8, 8)
+    rounds = [synth_inputs(1, shape, p["context_dim"], seed=20 + r) for r in range(3)]
+    ctx = [r_["context"].cuda() for r_ in rounds]
+    uctx = [r_["uc_context"].cuda() for r_ in rounds]
+    x_T = [r_["x"].cuda() for r_ in rounds]
+    img = rounds[0]["c_concat"][:, :, :1].cuda()
+    z0 = first_round_c_concat(img, 16)
+    assert z0.shape == (1, 4, 16, 8, 8) and torch.equal(z0[:, :, 7], img[:, :, 0])
+    t = torch.arange(16.0).view(1, 1, 16, 1, 1)
+    assert chain_c_concat(t)[0, 0, :, 0, 0].tolist() == [12., 13., 14., 15.] * 4
+    fs = torch.tensor([15], device="cuda")
+    torch.manual_seed(0)
+    outs = rollout(DDIMSampler(model), img, ctx, uctx, shape, steps=3, cfg_scale=4.0, eta=1.0, fs=fs, x_T=x_T)
+    assert len(outs) == 3 and all(torch.isfinite(o).all() for o in outs)
+    # by hand
+    torch.manual_seed(0)
+    s, z, ref = DDIMSampler(model), z0, []
+    for r in range(3):
+        x, _ = s.sample(S=3, batch_size=1, shape=shape, conditioning=dict(c_crossattn=[ctx[r]], c_concat=[z]),
+                        unconditional_conditioning=dict(c_crossattn=[uctx[r]], c_concat=[z]),
+                        unconditional_guidance_scale=4.0, eta=1.0, fs=fs, verbose=False,
+                        timestep_spacing="uniform_trailing", x_T=x_T[r], precision=torch.float32)
+        ref.append(x)
+        z = chain_c_concat(x.float())
+    for a, b_ in zip(outs, ref):
+        assert torch.equal(a, b_)
+    assert not torch.equal(outs[0], outs[1])
