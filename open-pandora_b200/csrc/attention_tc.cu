@@ -593,18 +593,25 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
       float lq[4] = {0.f, 0.f, 0.f, 0.f};
+      const float neg_m = -m_run;
       auto emit = [&](int c, const float (&x)[32]) {
         uint32_t w[16];
+        if (full) {                                       // no per-element key masking on all but the last tile
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fast_exp2(fmaf(x[i], p.scale_log2, -m_run));
-          float p1 = fast_exp2(fmaf(x[i + 1], p.scale_log2, -m_run));
-          if (!full) {
-            p0 = (c + i < valid) ? p0 : 0.f;
-            p1 = (c + i + 1 < valid) ? p1 : 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(fmaf(x[i], p.scale_log2, neg_m));
+            const float p1 = fast_exp2(fmaf(x[i + 1], p.scale_log2, neg_m));
+            lq[(i >> 1) & 3] += p0 + p1;
+            w[i >> 1] = pack_bf16(p0, p1);
           }
-          lq[(i >> 1) & 3] += p0 + p1;
-          w[i >> 1] = pack_bf16(p0, p1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c + i < valid) ? fast_exp2(fmaf(x[i], p.scale_log2, neg_m)) : 0.f;
+            const float p1 = (c + i + 1 < valid) ? fast_exp2(fmaf(x[i + 1], p.scale_log2, neg_m)) : 0.f;
+            lq[(i >> 1) & 3] += p0 + p1;
+            w[i >> 1] = pack_bf16(p0, p1);
+          }
         }
         tmem_st16(s_addr + (uint32_t)(c >> 1), w);       // 32 keys = 16 packed columns
       };
