@@ -431,6 +431,17 @@ __device__ __forceinline__ void tmem_st32f(uint32_t taddr, const float (&v)[32])
       : "memory");
 }
 
+// packed fp32x2 arithmetic (sm_100): one instruction for two lanes of the scale-and-shift and of the row sum
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %4};\nmov.b64 rc, {%5, %5};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
+  asm("{\n.reg .b64 ra, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rd, {%0, %1};\nadd.rn.f32x2 rd, rd, ra;\nmov.b64 {%0, %1}, rd;\n}"
+      : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
+
 constexpr int V2_STAGES = 4;
 constexpr int V2_SMEM = TILE_BYTES * (2 + 2 * V2_STAGES);      // Q x2 + (K, V) x4 = 160 KiB
 constexpr float V2_RESCALE_THRESHOLD = 8.0f;                    // log2 units
@@ -599,9 +610,10 @@ tc_attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (full) {                                       // no per-element key masking on all but the last tile
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = fast_exp2(fmaf(x[i], p.scale_log2, neg_m));
-            const float p1 = fast_exp2(fmaf(x[i + 1], p.scale_log2, neg_m));
-            lq[(i >> 1) & 3] += p0 + p1;
+            float e0, e1;
+            fma2(e0, e1, x[i], x[i + 1], p.scale_log2, neg_m);
+            const float p0 = fast_exp2(e0), p1 = fast_exp2(e1);
+            add2(lq[(i & 2)], lq[(i & 2) + 1], p0, p1);
             w[i >> 1] = pack_bf16(p0, p1);
           }
         } else {
