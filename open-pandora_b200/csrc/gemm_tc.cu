@@ -781,19 +781,31 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   return encode_tmap(out, PB_BF16, 128, base, rank, dims, strides_bytes, box, elem_strides);
 }
 
-// Exact 128-row brick bw x bh x bn with bw | W, bh | H, bn | N; prefers wide bricks (long contiguous
-// runs for the TMA unit).  Returns false when the tensor cannot be tiled exactly.
-static bool pick_brick(int W, int H, int N, int* bw, int* bh, int* bn) {
-  for (int w = W < BLOCK_M ? W : BLOCK_M; w >= 1; --w) {
-    if (W % w != 0 || BLOCK_M % w != 0) continue;
-    const int rest = BLOCK_M / w;
-    for (int h = H < rest ? H : rest; h >= 1; --h) {
-      if (H % h != 0 || rest % h != 0) continue;
-      const int n = rest / h;
-      if (n <= N && N % n == 0) { *bw = w; *bh = h; *bn = n; return true; }
+// 128-row brick bw x bh x bn (bw*bh*bn = 128, each extent a power of two no larger than the tensor's).  Exact
+// tilings (bw | W, bh | H, bn | N) are preferred, widest bw first (long contiguous runs for the TMA unit).  When
+// none exists — 9x16 images with 4 frames per rank, 36 pixels per rank under sequence parallelism — the brick that
+// needs the fewest tiles is taken and the ragged edge tiles hang over the tensor: the TMA unit zero-fills the rows it
+// loads from outside and clips the rows it stores there, so the tile arithmetic is unchanged (the hang-over is wasted
+// tensor work, still an order of magnitude faster than the CUDA-core path).
+static bool pick_brick(int W, int H, int N, int* bw, int* bh, int* bn, bool* exact) {
+  long best_tiles = -1;
+  bool best_exact = false;
+  for (int w = BLOCK_M; w >= 1; w >>= 1) {
+    if (w > W) continue;
+    for (int h = BLOCK_M / w; h >= 1; h >>= 1) {
+      if (h > H) continue;
+      const int n = BLOCK_M / (w * h);
+      if (n > N) continue;
+      const bool ex = W % w == 0 && H % h == 0 && N % n == 0;
+      const long tiles = (long)((W + w - 1) / w) * ((H + h - 1) / h) * ((N + n - 1) / n);
+      // exact beats inexact; then fewer tiles; then (loop order) wider w, taller h
+      if (best_tiles < 0 || (ex && !best_exact) || (ex == best_exact && tiles < best_tiles)) {
+        best_tiles = tiles; best_exact = ex; *bw = w; *bh = h; *bn = n;
+      }
     }
   }
-  return false;
+  if (exact) *exact = best_exact;
+  return best_tiles > 0;
 }
 
 static int num_sms();
@@ -987,11 +999,12 @@ static int tc_plan(const pb_gemm_args* a, TcPlan* pl) {
     const int s2 = a->stride;
     const int W = a->out_w, H = a->out_h, n_img = (int)(a->M / ((int64_t)H * W));
     p.W = W; p.H = H; p.cstride = s2;
-    if (!pick_brick(W, H, n_img, &p.bw, &p.bh, &p.bn_img))
-      TC_UNSUPPORTED("pb_tc_gemm: %dx%d x %d images has no exact 128-row brick", H, W, n_img);
+    bool exact = false;
+    if (!pick_brick(W, H, n_img, &p.bw, &p.bh, &p.bn_img, &exact))
+      TC_UNSUPPORTED("pb_tc_gemm: %dx%d x %d images cannot hold a 128-row brick", H, W, n_img);
     if (s2 * p.bw > 256 || s2 * p.bh > 256) TC_UNSUPPORTED("pb_tc_gemm: strided box exceeds the TMA box limit");
-    p.tiles_x = W / p.bw; p.tiles_y = H / p.bh;
-    p.m_tiles = p.tiles_x * p.tiles_y * (n_img / p.bn_img);
+    p.tiles_x = (W + p.bw - 1) / p.bw; p.tiles_y = (H + p.bh - 1) / p.bh;
+    p.m_tiles = p.tiles_x * p.tiles_y * ((n_img + p.bn_img - 1) / p.bn_img);
     pl->a_rank = 4;
     pl->adims[0] = (uint64_t)cin; pl->adims[1] = (uint64_t)a->in_w; pl->adims[2] = (uint64_t)a->in_h; pl->adims[3] = (uint64_t)n_img;
     pl->astr[0] = (uint64_t)a->lda * esz; pl->astr[1] = pl->astr[0] * a->in_w; pl->astr[2] = pl->astr[1] * a->in_h;
@@ -1001,14 +1014,16 @@ static int tc_plan(const pb_gemm_args* a, TcPlan* pl) {
     pl->odims[0] = (uint64_t)W; pl->odims[1] = (uint64_t)H; pl->odims[2] = (uint64_t)n_img;
     pl->obox[0] = (uint32_t)p.bw; pl->obox[1] = (uint32_t)p.bh; pl->obox[2] = (uint32_t)p.bn_img;
     p.n_outer = n_img;
-    slab_ok = ((int64_t)W * H) % 32 == 0 && ((p.bw % 32 == 0) || (p.bw == W && 32 % p.bw == 0 && p.bh % (32 / p.bw) == 0));
+    slab_ok = exact && ((int64_t)W * H) % 32 == 0 && ((p.bw % 32 == 0) || (p.bw == W && 32 % p.bw == 0 && p.bh % (32 / p.bw) == 0));
   } else {
     p.taps = 3;
     const int HW = a->frame_rows, T = a->frames, nb = (int)(a->M / ((int64_t)HW * T));
     p.W = HW; p.H = T; p.bn_img = 1;
     int one = 1;
-    if (!pick_brick(HW, T, 1, &p.bw, &p.bh, &one)) TC_UNSUPPORTED("pb_tc_gemm: %d pixels x %d frames has no exact 128-row brick", HW, T);
-    p.tiles_x = HW / p.bw; p.tiles_y = T / p.bh;
+    bool exact = false;
+    if (!pick_brick(HW, T, 1, &p.bw, &p.bh, &one, &exact))
+      TC_UNSUPPORTED("pb_tc_gemm: %d pixels x %d frames cannot hold a 128-row brick", HW, T);
+    p.tiles_x = (HW + p.bw - 1) / p.bw; p.tiles_y = (T + p.bh - 1) / p.bh;
     p.m_tiles = p.tiles_x * p.tiles_y * nb;
     pl->a_rank = 4;
     pl->adims[0] = (uint64_t)cin; pl->adims[1] = (uint64_t)HW; pl->adims[2] = (uint64_t)T; pl->adims[3] = (uint64_t)nb;
@@ -1017,7 +1032,7 @@ static int tc_plan(const pb_gemm_args* a, TcPlan* pl) {
     pl->odims[0] = (uint64_t)HW; pl->odims[1] = (uint64_t)T; pl->odims[2] = (uint64_t)nb;
     pl->obox[0] = (uint32_t)p.bw; pl->obox[1] = (uint32_t)p.bh; pl->obox[2] = 1;
     p.n_outer = nb;
-    slab_ok = ((int64_t)HW * T) % 32 == 0 && ((p.bw % 32 == 0) || (p.bw == HW && 32 % p.bw == 0 && p.bh % (32 / p.bw) == 0));
+    slab_ok = exact && ((int64_t)HW * T) % 32 == 0 && ((p.bw % 32 == 0) || (p.bw == HW && 32 % p.bw == 0 && p.bh % (32 / p.bw) == 0));
   }
   const int n_cols = geglu ? (int)(a->N / 2) : (int)a->N;   // output columns
   pl->n_cols = n_cols;
@@ -1028,7 +1043,9 @@ static int tc_plan(const pb_gemm_args* a, TcPlan* pl) {
   // split-K (deterministic: fp32 partials in the caller's workspace + a fold kernel) when the grid is tiny
   const int k_iters = p.taps * p.k_chunks;
   p.splits = 1; p.kps = k_iters;
-  const int want_splits = geglu ? 1 : pick_splits(p.m_tiles * p.n_tiles, k_iters);
+  // split-K partials are consecutive copies of the output: an image-ragged brick would spill into the next copy
+  const bool n_ragged = a->a_mode == PB_A_CONV3X3 && p.n_outer % p.bn_img != 0;
+  const int want_splits = (geglu || n_ragged) ? 1 : pick_splits(p.m_tiles * p.n_tiles, k_iters);
   pl->c_base = a->c; pl->ldc = a->ldc; pl->c_dtype = a->c_dtype;
   if (want_splits > 1 && a->workspace && (reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0 &&
       a->workspace_bytes >= (int64_t)want_splits * a->M * a->N * (int64_t)sizeof(float)) {
@@ -1053,7 +1070,7 @@ static int tc_plan(const pb_gemm_args* a, TcPlan* pl) {
   // the tile = a sub-brick of the A box; conv stride 2 keeps the plain pair kernel.
   p.mc = 1;
   static const int mc_cap = []() { const char* e = getenv("PB_TC_MC"); return e ? atoi(e) : 1; }();
-  if (p.pair && !(a->a_mode == PB_A_CONV3X3 && a->stride != 1)) {
+  if (p.pair && mc_cap > 1 && !(a->a_mode == PB_A_CONV3X3 && a->stride != 1) && (long)p.m_tiles * BLOCK_M == a->M) {
     for (int mc = 4; mc >= 2; mc >>= 1) {
       if (mc > mc_cap || p.n_tiles % mc != 0) continue;
       // enough clusters to fill the machine

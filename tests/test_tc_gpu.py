@@ -194,6 +194,39 @@ def test_tc_conv3x3_stride2_by_tma_element_strides(abi, n, cin, cout, H, W):
     assert rel_l2(c, ref.permute(0, 2, 3, 1).reshape(n * oh * ow, cout)) < 1e-5
 
 
+@pytest.mark.parametrize("n,cin,cout,H,W", [(4, 64, 128, 9, 16), (8, 128, 64, 9, 16), (3, 64, 64, 18, 32), (2, 64, 64, 36, 64),
+                                            (5, 64, 64, 10, 16)])
+def test_tc_conv3x3_ragged_bricks(abi, n, cin, cout, H, W):
+    """Images that no exact 128-row brick tiles (576x1024 latents sharded over 4 ranks: 9x16 x 4 frames): edge tiles
+    hang over the tensor, the copy engine zero-fills / clips them."""
+    x = rnd(n, cin, H, W, seed=51, dtype=BF)
+    w = rnd(cout, cin, 3, 3, seed=52, dtype=BF, scale=(9 * cin) ** -0.5)
+    bias, res = rnd(cout, seed=53), rnd(n * H * W, cout, seed=54)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    rows = x.permute(0, 2, 3, 1).reshape(n * H * W, cin).contiguous()
+    wide = torch.full((n * H * W + 64, cout), 7.0, device="cuda")           # guard rows after the tensor
+    c = wide[:n * H * W]
+    c.fill_(float("nan"))
+    assert abi.gemm(rows, conv_weight_rows(w), c, bias=bias, residual=res, mode=abi.A_CONV3X3,
+                    conv=(cin, H, W, H, W, 1, 0), tc=True), "expected the TMA path to take this shape"
+    assert rel_l2(c, ref.permute(0, 2, 3, 1).reshape(n * H * W, cout) + res.double()) < 1e-5
+    assert float((wide[n * H * W:] - 7.0).abs().max()) == 0
+
+
+@pytest.mark.parametrize("nb,C,HW,T", [(1, 64, 36, 16), (2, 128, 36, 16), (1, 64, 144, 16), (1, 64, 100, 8)])
+def test_tc_convt3_ragged_bricks(abi, nb, C, HW, T):
+    x = rnd(nb, C, T, HW, seed=55, dtype=BF)
+    w = rnd(C, C, 3, seed=56, dtype=BF, scale=(3 * C) ** -0.5)
+    bias = rnd(C, seed=57)
+    ref = F.conv1d(x.double().permute(0, 3, 1, 2).reshape(nb * HW, C, T), w.double(), bias.double(), padding=1)
+    ref = ref.reshape(nb, HW, C, T).permute(0, 3, 1, 2).reshape(nb * T * HW, C)
+    rows = x.permute(0, 2, 3, 1).reshape(nb * T * HW, C).contiguous()
+    wr = w.permute(0, 2, 1).reshape(C, 3 * C).contiguous()
+    c = torch.full((nb * T * HW, C), float("nan"), device="cuda")
+    assert abi.gemm(rows, wr, c, bias=bias, mode=abi.A_CONVT3, convt=(C, T, HW), tc=True)
+    assert rel_l2(c, ref) < 1e-5
+
+
 def _slab_stats(c):
     """fp64 reference of pb_gemm_args.colstats: per 32-row slab, per column (sum, sumsq)."""
     M, N = c.shape
