@@ -341,7 +341,10 @@ class _Runner:
         tensor for its statistics (pb_gemm_args.colstats)."""
         t = self.new(rows, cols, torch.float32)
         t._cs = self.new(rows // 32, 2 * cols, torch.float32) if (self.use_tc and rows % 32 == 0) else None
-        t._cs_valid, t._cs_parts = False, [t]
+        # validity flags live in plain dicts: a tensor attribute that refers back to the tensor or to one of its
+        # views forms a reference cycle through the C++ side that the garbage collector cannot break (a leak)
+        t._cs_state = {"valid": False}
+        t._cs_states = [t._cs_state]
         return t
 
     def trunk_cols(self, t, c0, c1):
@@ -349,7 +352,8 @@ class _Runner:
         their half of a skip concatenation (openaimodel3d.py:600) in place instead of copying it there."""
         v = t[:, c0:c1]
         v._cs = None if t._cs is None else t._cs[:, 2 * c0:2 * c1]
-        v._cs_valid, v._cs_parts = False, [v]
+        v._cs_state = {"valid": False}
+        v._cs_states = [v._cs_state]
         return v
 
     # ---- packed weights -----------------------------------------------------------------------
@@ -409,7 +413,7 @@ class _Runner:
             cs = getattr(c, "_cs", None) if stats else None
             done = abi.gemm(a, w, c, tc=True, M=M, colstats=cs, **kw)
             if done == 2:
-                c._cs_valid = True
+                c._cs_state["valid"] = True
         if not done:
             if kw.get("geglu"):
                 kw = dict(kw, geglu=False)
@@ -445,8 +449,8 @@ class _Runner:
                              self.sp.all_reduce_sum, rows * self.sp.P)
         else:
             # statistics left behind by the producer(s) of x (both halves for a skip concatenation)
-            cs, parts = getattr(x, "_cs", None), getattr(x, "_cs_parts", None)
-            if cs is None or not parts or rows % 32 or not all(getattr(q, "_cs_valid", False) for q in parts):
+            cs, states = getattr(x, "_cs", None), getattr(x, "_cs_states", None)
+            if cs is None or not states or rows % 32 or not all(q["valid"] for q in states):
                 cs = None
             abi.groupnorm(x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu,
                           colstats=cs)
@@ -739,7 +743,8 @@ class _Runner:
                 raise TypeError(type(layer))
         if out is not None and h is not out:
             abi.copy_rows(h, out)
-            out._cs_valid = False
+            if hasattr(out, "_cs_state"):
+                out._cs_state["valid"] = False
             h = out
         return h, H, W
 
@@ -796,7 +801,7 @@ class _Runner:
             c_tot, c_s = m.output_blocks[k][0].channels, self._seq_out_channels(seq)
             cat = self.new_trunk(b * T * Ho * Wo, c_tot)
             hv, sv = self.trunk_cols(cat, 0, c_tot - c_s), self.trunk_cols(cat, c_tot - c_s, c_tot)
-            cat._cs_parts = [hv, sv]
+            cat._cs_states = [hv._cs_state, sv._cs_state]
             cats[k] = (cat, hv, sv)
             if i == 0 and m.addition_attention:
                 h, H, W = self.run_block(seq, h, H, W)

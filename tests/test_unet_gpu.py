@@ -190,3 +190,31 @@ def test_rollout_chains_rounds_like_pandora():
     for a, b_ in zip(outs, ref):
         assert torch.equal(a, b_)
     assert not torch.equal(outs[0], outs[1])
+
+
+def test_forward_does_not_leak_device_memory():
+    """The runner hangs bookkeeping on its trunk tensors; none of it may keep a forward's activations alive
+    (a tensor attribute referring to a view of the same storage would: the cycle runs through C++ and is never
+    collected)."""
+    import gc
+    from pandora_b200 import UNetModel, config
+    from pandora_b200.synthetic import randomize_module_, synth_inputs
+    p = config.small_unet()
+    m = randomize_module_(UNetModel(**p).eval(), 3).to(device="cuda", dtype=torch.bfloat16)
+    inp = {k: v.cuda() for k, v in synth_inputs(2, (4, 16, 16, 16), p["context_dim"], seed=1).items()}
+    t = torch.tensor([499, 19], device="cuda")
+    run = lambda: m(inp["x"], t, context=inp["context"], x_concat=[inp["c_concat"]])
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    gc.disable()
+    try:
+        base = torch.cuda.memory_allocated()
+        for _ in range(6):
+            y = run()
+        del y
+        torch.cuda.synchronize()
+        grown = torch.cuda.memory_allocated() - base
+    finally:
+        gc.enable()
+    assert grown < (1 << 20), f"{grown / 2**20:.1f} MiB still allocated after 6 forwards"
