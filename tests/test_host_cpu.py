@@ -96,3 +96,30 @@ def test_product_never_imports_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_rollout_round_chaining_matches_pandora_tiling():
+    """model.py:690-701,1179-1187: round 1 repeats one image latent over all frames; later rounds tile the last four
+    frames (einops '(repeat t)' order f0 f1 f2 f3 f0 ...)."""
+    from pandora_b200.rollout import chain_c_concat, first_round_c_concat
+    lat = torch.arange(2 * 3 * 16 * 2 * 2, dtype=torch.float32).reshape(2, 3, 16, 2, 2)
+    z = chain_c_concat(lat)
+    assert z.shape == lat.shape
+    for t in range(16):
+        assert torch.equal(z[:, :, t], lat[:, :, 12 + t % 4])
+    img = torch.randn(2, 3, 1, 2, 2)
+    z0 = first_round_c_concat(img, 16)
+    assert z0.shape == (2, 3, 16, 2, 2) and all(torch.equal(z0[:, :, t], img[:, :, 0]) for t in range(16))
+    assert torch.equal(first_round_c_concat(img[:, :, 0], 16), z0)
+
+
+def test_sampler_batches_cfg_branches_by_default():
+    """ddim.py:233-234 are two sequential forwards; the native sampler evaluates them as one doubled batch unless a
+    branch split / sequence-parallel mode is active or batch_cfg is switched off."""
+    from pandora_b200 import DDIMSampler
+
+    class _M:
+        num_timesteps = 1000
+    s = DDIMSampler(_M())
+    assert s.batch_cfg is True and s.cfg_parallel is None and s.replica_group is None
+    assert s._can_batch_cfg({"c_crossattn": []}, {"c_crossattn": []}) is False      # no native U-Net underneath
