@@ -123,3 +123,42 @@ def test_sampler_batches_cfg_branches_by_default():
     s = DDIMSampler(_M())
     assert s.batch_cfg is True and s.cfg_parallel is None and s.replica_group is None
     assert s._can_batch_cfg({"c_crossattn": []}, {"c_crossattn": []}) is False      # no native U-Net underneath
+
+
+REF_DC = "/root/reference/DynamiCrafter"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_DC), reason="the reference tree only exists in the build container")
+def test_drop_in_against_the_live_reference():
+    """With the reference importable: `install()` makes the reference's dotted path resolve to the native class
+    (`instantiate_from_config`, DynamiCrafter/utils/utils.py:27-42), the native module takes the reference module's
+    state dict with strict=True, and `from_reference` shares the reference's Parameter objects."""
+    import importlib
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path[:0] = ["%s", "%s", "%s"]
+import torch
+import pandora_b200
+from pandora_b200 import config
+ref_mod = __import__("lvdm.modules.networks.openaimodel3d", fromlist=["UNetModel"])
+RefUNet = ref_mod.UNetModel
+p = config.small_unet()
+ref = RefUNet(**p)
+nat = pandora_b200.UNetModel(**p)
+missing = nat.load_state_dict(ref.state_dict(), strict=True)
+assert [k for k in ref.state_dict()] == [k for k in nat.state_dict()], "key order / names differ"
+shared = pandora_b200.UNetModel.from_reference(ref, **p)
+assert all(a is b for a, b in zip(shared.parameters(), ref.parameters()))
+patched = pandora_b200.install()
+assert ref_mod.UNetModel is pandora_b200.UNetModel and any("openaimodel3d" in n for n in patched), patched
+from utils.utils import instantiate_from_config
+obj = instantiate_from_config({"target": "lvdm.modules.networks.openaimodel3d.UNetModel", "params": p})
+assert type(obj) is pandora_b200.UNetModel
+ddim_mod = __import__("lvdm.models.samplers.ddim", fromlist=["DDIMSampler"])
+assert ddim_mod.DDIMSampler is pandora_b200.DDIMSampler
+print("DROP_IN_OK")
+''' % (REF_DC, os.path.join(ROOT, "open-pandora_b200"), ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "DROP_IN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
