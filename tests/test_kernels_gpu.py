@@ -291,3 +291,17 @@ def test_ddim_cfg_step_bit_exact_vs_torch_fp32(abi, phi, cfg):
         assert rel_l2(xp, rp) < 1e-6 and rel_l2(x0, r0) < 1e-6
     else:
         assert torch.equal(x0, r0) and torch.equal(xp, rp)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1280, 320), (2, 20160, 1280), (8, 1000, 1284), (3, 36, 64)])
+def test_gemm_few_rows_embedding_path(abi, M, N, K):
+    """The timestep / fps embedding MLPs and the folded ResBlock emb projections (1-2 rows): warp-per-column GEMV."""
+    a, w, bias = rnd(M, K, seed=70), rnd(N, K, seed=71, scale=K ** -0.5), rnd(N, seed=72)
+    big = torch.zeros(M, N + 8, device="cuda")
+    c = big[:, 4:4 + N]
+    assert abi.gemm(a, w, c, bias=bias)
+    assert rel_l2(c, a.double() @ w.double().t() + bias.double()) < 2e-6
+    assert float(big[:, :4].abs().max()) == 0 and float(big[:, 4 + N:].abs().max()) == 0
+    c2 = torch.empty(M, N, device="cuda")
+    assert abi.gemm(a, w, c2)
+    assert rel_l2(c2, a.double() @ w.double().t()) < 2e-6
