@@ -227,7 +227,9 @@ int pb_rows_to_video(const float* rows, int64_t ld, void* out, int32_t out_dtype
  * Per-step scalars are read ON THE DEVICE from `tables` [n_steps, PB_DDIM_NCOEF] at row
  * *step_index (a device int32 the kernel post-increments when `advance`), so the 50-step loop has
  * no host<->device scalar traffic (the reference does 4-6 .item()-style reads per step,
- * ddim.py:263-266,274-275).  v_uncond may be NULL (no CFG).  Tensors are flat [batch, n] fp32.    */
+ * ddim.py:263-266,274-275).  v_uncond may be NULL (no CFG).  Tensors are flat [batch, n] fp32.
+ * x_prev MAY alias x (in-place update: every element is read once and then written by the same thread);
+ * no other pair of arguments may overlap.                                                          */
 enum { PB_DDIM_SQRT_AC = 0,      /* sqrt_alphas_cumprod[t]            (bf16 buffer value)           */
        PB_DDIM_SQRT_OMAC = 1,    /* sqrt_one_minus_alphas_cumprod[t]  (bf16 buffer value)           */
        PB_DDIM_SQRT_A_PREV = 2,  /* a_prev.sqrt()                                                   */
@@ -241,6 +243,45 @@ int pb_ddim_cfg_step(const float* x, const float* v_cond, const float* v_uncond,
                      float guidance_rescale, float temperature, const float* tables,
                      int32_t* step_index, int32_t advance, void* ws, size_t ws_bytes,
                      pb_stream_t stream);
+
+
+/* ---- sequence-parallel communication (one clip across P GPUs) ---------------------------------
+ * No reference counterpart: the reference never shards a clip.  Frames are sharded for the
+ * per-frame layers (modules/networks/openaimodel3d.py:570) and pixels for the per-pixel layers
+ * (modules/attention.py:369-372); these two entry points are the data-path exchanges between the shardings,
+ * written as kernels over peer-addressable memory (NVLink) instead of NCCL calls.
+ *
+ * pb_sp_barrier: flags[d] = rank d's flag array (P x uint32, peer-addressable), epoch = this rank's private
+ * {epoch, ticket} pair (2 x uint32, zero-initialised).  epoch == NULL => no device-side barrier: the caller orders
+ * the ranks itself (single-process virtual ranks with host barriers; tests).                        */
+#define PB_SP_MAX_RANKS 16
+typedef struct pb_sp_barrier {
+  uint32_t* flags[PB_SP_MAX_RANKS];
+  uint32_t* epoch;
+} pb_sp_barrier;
+
+/* Frame <-> pixel re-shard as ONE pull kernel.  Rows are [samples][frames][pixels] x cols.
+ *   direction 0 (frames -> pixels): src[s] = rank s's frame-sharded rows (samples, t_local, hw_local*P);
+ *                                   dst    = this rank's pixel-sharded rows (samples, t_local*P, hw_local)
+ *   direction 1 (pixels -> frames): src[s] = rank s's pixel-sharded rows; dst = this rank's frame-sharded rows
+ * src[rank] is this rank's own send buffer.  ld_* in elements; cols * elem_bytes must be a multiple of 16.   */
+typedef struct pb_sp_reshard_args {
+  const void* src[PB_SP_MAX_RANKS];
+  void* dst;
+  int64_t ld_src, ld_dst, cols;
+  int64_t samples, t_local, hw_local;
+  int32_t P, rank, direction, elem_bytes;
+  pb_sp_barrier barrier;
+} pb_sp_reshard_args;
+int pb_sp_reshard(const pb_sp_reshard_args* args, pb_stream_t stream);
+
+/* Clip-wide GroupNorm statistics across ranks: sums[r] = rank r's fp64 (sum, sumsq) per (instance, group)
+ * (pb_groupnorm_sums output, in a peer-addressable slot); adds the P partials in rank order and writes
+ * scale_shift [n_inst, 2, C] for pb_groupnorm_apply.  count = elements per (instance, group) over ALL ranks.
+ * Replaces one NCCL all-reduce per temporal GroupNorm (openaimodel3d.py:259-268, attention.py:331).          */
+int pb_sp_groupnorm_affine(const double* const* sums, int32_t P, int32_t rank, const pb_sp_barrier* barrier,
+                           int64_t n_inst, int64_t C, int32_t groups, double count, float eps, const float* gamma,
+                           const float* beta, float* scale_shift, pb_stream_t stream);
 
 #ifdef __cplusplus
 }

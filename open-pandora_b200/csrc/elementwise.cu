@@ -150,8 +150,9 @@ ddim_stats_kernel(const float* __restrict__ vc, const float* __restrict__ vu, in
 //   x0  *= rescale                                              ddim.py:273-277
 //   xp   = sqrt(a_prev)*x0 + dir*e + sigma*noise*temperature    ddim.py:282-288
 __global__ void __launch_bounds__(256)
-ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ vc, const float* __restrict__ vu,
-                   const float* __restrict__ noise, float* __restrict__ xp, float* __restrict__ x0o,
+ddim_update_kernel(const float* x /* may alias xp: in-place update of the graph's static latent */,
+                   const float* __restrict__ vc, const float* __restrict__ vu,
+                   const float* __restrict__ noise, float* xp, float* __restrict__ x0o,
                    int64_t n, float s, float phi, float temperature, const float* __restrict__ tables,
                    const int32_t* __restrict__ step_index, const double* __restrict__ ws) {
   const int b = blockIdx.y;

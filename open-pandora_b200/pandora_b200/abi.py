@@ -51,6 +51,23 @@ class AttnArgs(C.Structure):
     ]
 
 
+SP_MAX_RANKS = 16
+
+
+class SpBarrier(C.Structure):
+    _fields_ = [("flags", C.c_void_p * SP_MAX_RANKS), ("epoch", C.c_void_p)]
+
+
+class SpReshardArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p * SP_MAX_RANKS), ("dst", C.c_void_p),
+        ("ld_src", C.c_int64), ("ld_dst", C.c_int64), ("cols", C.c_int64),
+        ("samples", C.c_int64), ("t_local", C.c_int64), ("hw_local", C.c_int64),
+        ("P", C.c_int32), ("rank", C.c_int32), ("direction", C.c_int32), ("elem_bytes", C.c_int32),
+        ("barrier", SpBarrier),
+    ]
+
+
 # every symbol include/pandora_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _i32, _f, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
 SYMBOLS = {
@@ -82,6 +99,9 @@ SYMBOLS = {
     "pb_timestep_embedding": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "pb_video_to_rows": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _vp, _i64, _i64, _i64, _i64, _vp]),
     "pb_rows_to_video": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp]),
+    "pb_sp_reshard": (C.c_int, [C.POINTER(SpReshardArgs), _vp]),
+    "pb_sp_groupnorm_affine": (C.c_int, [C.POINTER(C.c_void_p), _i32, _i32, C.POINTER(SpBarrier), _i64, _i64, _i32,
+                                         C.c_double, _f, _vp, _vp, _vp, _vp]),
     "pb_ddim_ws_bytes": (_sz, [_i64]),
     "pb_ddim_cfg_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _vp, _vp, _i32, _vp, _sz, _vp]),
 }
@@ -303,6 +323,65 @@ def groupnorm_sp(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, all_reduce
     all_reduce(sums)
     _check(lib.pb_groupnorm_affine(sums.data_ptr(), n_inst, Cc, groups, float(global_rows * (Cc // groups)), eps,
                                    gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), st), "pb_groupnorm_affine")
+    _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc,
+                                  stats.data_ptr(), int(silu), st), "pb_groupnorm_apply")
+    launches += 4
+
+
+def _sp_barrier(flag_ptrs, epoch_ptr):
+    b = SpBarrier()
+    if epoch_ptr:
+        for i, f in enumerate(flag_ptrs):
+            b.flags[i] = f
+        b.epoch = epoch_ptr
+    return b
+
+
+def sp_reshard(src_ptrs, ld_src, dst, direction, rank, samples, t_local, hw_local, cols, elem_bytes,
+               flag_ptrs=None, epoch_ptr=None):
+    """Pull this rank's share of every rank's send buffer (`src_ptrs`, device addresses valid on THIS device) into the
+    row view `dst`: direction 0 = frames -> pixels, 1 = pixels -> frames (see pb_sp_reshard)."""
+    global launches
+    a = SpReshardArgs()
+    P = len(src_ptrs)
+    for i, p in enumerate(src_ptrs):
+        a.src[i] = p
+    a.dst, a.ld_dst = _rows(dst)
+    a.ld_src, a.cols = ld_src, cols
+    a.samples, a.t_local, a.hw_local = samples, t_local, hw_local
+    a.P, a.rank, a.direction, a.elem_bytes = P, rank, direction, elem_bytes
+    a.barrier = _sp_barrier(flag_ptrs, epoch_ptr)
+    nb = samples * t_local * P * hw_local * cols * elem_bytes
+    tok = _tick("sp_reshard", 0, 2 * nb, f"P{P} dir{direction} rows{samples * t_local * P * hw_local} C{cols}")
+    _check(load().pb_sp_reshard(C.byref(a), _stream()), "pb_sp_reshard")
+    _tock(tok)
+    launches += 1
+
+
+def groupnorm_sp_peers(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, my_sums, sums_ptrs, rank, global_rows,
+                       flag_ptrs=None, epoch_ptr=None, before_reduce=None, groups=32):
+    """GroupNorm whose statistics span ranks, without NCCL: local fp64 sums into this rank's peer-visible slot
+    (`my_sums`), one kernel that adds every rank's partials (`sums_ptrs`) behind a flag barrier, apply."""
+    global launches
+    lib = load()
+    Cc = x.shape[1]
+    ws_bytes = lib.pb_groupnorm_ws_bytes(n_inst, rows_per_inst, Cc)
+    ws = torch.empty(ws_bytes // 4 + n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
+    stats = ws[ws_bytes // 4:]
+    xp, ldx = _rows(x)
+    yp, ldy = _rows(y)
+    st = _stream()
+    assert my_sums.dtype == torch.float64 and my_sums.numel() >= n_inst * groups * 2
+    _check(lib.pb_groupnorm_sums(xp, dt(x), ldx, n_inst, rows_per_inst, Cc, groups, my_sums.data_ptr(), ws.data_ptr(),
+                                 ws_bytes, st), "pb_groupnorm_sums")
+    if before_reduce is not None:
+        before_reduce()
+    P = len(sums_ptrs)
+    arr = (C.c_void_p * P)(*sums_ptrs)
+    bar = _sp_barrier(flag_ptrs, epoch_ptr)
+    _check(lib.pb_sp_groupnorm_affine(arr, P, rank, C.byref(bar), n_inst, Cc, groups,
+                                      float(global_rows * (Cc // groups)), eps, gamma.data_ptr(), beta.data_ptr(),
+                                      stats.data_ptr(), st), "pb_sp_groupnorm_affine")
     _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc,
                                   stats.data_ptr(), int(silu), st), "pb_groupnorm_apply")
     launches += 4

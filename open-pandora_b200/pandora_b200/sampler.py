@@ -102,30 +102,68 @@ class GraphedCFGStep:
         self.cfg = uncond is not None and cfg_scale != 1.0
         self.cfg_scale, self.rescale, self.temperature = float(cfg_scale), float(guidance_rescale), float(temperature)
         f32 = torch.float32
+        b = shape[0]
         self.x = torch.zeros(shape, dtype=f32, device=dev)
         self.noise = torch.zeros(shape, dtype=f32, device=dev)
         self.pred_x0 = torch.zeros(shape, dtype=f32, device=dev)
-        self.ts = torch.zeros((shape[0],), dtype=torch.long, device=dev)
         self.step_index = torch.zeros((1,), dtype=torch.int32, device=dev)
-        self.table = table.flip(0).contiguous()          # row i = i-th executed step (index S-1-i)
-        self.ws = torch.zeros(4 * shape[0], dtype=torch.float64, device=dev)
-        self.fs = fs
-        cat = lambda c: c[0] if len(c) == 1 else torch.cat(list(c), 1)
-        self.ctx_c, self.z_c = cat(cond["c_crossattn"]), cat(cond["c_concat"])
-        self.ctx_u = self.z_u = None
-        if self.cfg:
-            self.ctx_u, self.z_u = cat(uncond["c_crossattn"]), cat(uncond["c_concat"])
+        self.table = torch.zeros_like(table)             # row i = i-th executed step (index S-1-i)
+        self.ws = torch.zeros(4 * b, dtype=torch.float64, device=dev)
         self.batched = (self.cfg and sampler.batch_cfg and sampler.cfg_parallel is None
-                        and getattr(unet, "sequence_parallel", None) is None)
+                        and (getattr(unet, "sequence_parallel", None) is None
+                             or getattr(unet.sequence_parallel, "batch_ok", False)))
+        # Every tensor the captured graph reads is OWNED by this object (static addresses): conditioning of a later
+        # `sample()` call is copied in (`load`), so one capture serves every round of a rollout.
+        ctx_c, z_c, ctx_u, z_u = self._sources(cond, uncond)
+        nb = 2 * b if self.batched else b
+        own = lambda t, n: torch.zeros((n, *t.shape[1:]), dtype=t.dtype, device=dev)
+        self.ts = torch.zeros((nb,), dtype=torch.long, device=dev)
+        self.fs_b = None if fs is None else torch.zeros((nb,), dtype=torch.long, device=dev)
         if self.batched:
-            b = shape[0]
             self.x2 = torch.zeros((2 * b, *shape[1:]), dtype=f32, device=dev)
-            self.ts = torch.zeros((2 * b,), dtype=torch.long, device=dev)
-            self.ctx_b = torch.cat([self.ctx_c, self.ctx_u], 0).contiguous()
-            self.z_b = torch.cat([self.z_c, self.z_u], 0).contiguous()
-            self.fs_b = None if fs is None else torch.cat([fs, fs], 0)
+            self.ctx_b, self.z_b = own(ctx_c, 2 * b), own(z_c, 2 * b)
+            self.ctx_c, self.z_c, self.ctx_u, self.z_u = self.ctx_b[:b], self.z_b[:b], self.ctx_b[b:], self.z_b[b:]
+        else:
+            self.ctx_c, self.z_c = own(ctx_c, b), own(z_c, b)
+            self.ctx_u = self.z_u = None
+            if self.cfg:
+                self.ctx_u, self.z_u = own(ctx_u, b), own(z_u, b)
         self.graph = None
         self.launches_per_step = 0
+        self.load(cond, uncond, fs, table)
+
+    @staticmethod
+    def _sources(cond, uncond):
+        cat = lambda c: c[0] if len(c) == 1 else torch.cat(list(c), 1)
+        ctx_c, z_c = cat(cond["c_crossattn"]), cat(cond["c_concat"])
+        ctx_u = z_u = None
+        if uncond is not None:
+            ctx_u, z_u = cat(uncond["c_crossattn"]), cat(uncond["c_concat"])
+        return ctx_c, z_c, ctx_u, z_u
+
+    def signature(self):
+        """What a later call must match to reuse this capture (shapes / dtypes of everything the graph reads)."""
+        sig = lambda t: None if t is None else (tuple(t.shape), t.dtype)
+        return (tuple(self.x.shape), self.cfg, self.cfg_scale, self.rescale, self.temperature, tuple(self.table.shape),
+                sig(self.ctx_c), sig(self.z_c), sig(self.ctx_u), sig(self.z_u), self.fs_b is None, self.batched)
+
+    def load(self, cond, uncond, fs, table):
+        """Copy the conditioning / schedule of a `sample()` call into the static buffers (host or device sources)
+        and, once captured, recompute the cached context K|V projections in place."""
+        ctx_c, z_c, ctx_u, z_u = self._sources(cond, uncond)
+        self.table.copy_(table.flip(0), non_blocking=True)
+        self.ctx_c.copy_(ctx_c, non_blocking=True)
+        self.z_c.copy_(z_c, non_blocking=True)
+        if self.cfg:
+            self.ctx_u.copy_(ctx_u, non_blocking=True)
+            self.z_u.copy_(z_u, non_blocking=True)
+        if self.fs_b is not None:
+            b = self.x.shape[0]
+            self.fs_b[:b].copy_(fs, non_blocking=True)
+            if self.batched:
+                self.fs_b[b:].copy_(fs, non_blocking=True)
+        if self.graph is not None:
+            self.refresh_conditioning()
 
     def _body(self):
         cfgp = self.sampler.cfg_parallel if self.cfg else None
@@ -138,10 +176,10 @@ class GraphedCFGStep:
             v_c, v_u = v[:b], v[b:]
         elif cfgp is not None:                 # one branch per rank, then all-gather v
             ctx, z = cfgp.my_branch((self.ctx_c, self.z_c), (self.ctx_u, self.z_u))
-            v_c, v_u = cfgp.exchange(self.unet(self.x, self.ts, context=ctx, fs=self.fs, x_concat=[z]))
+            v_c, v_u = cfgp.exchange(self.unet(self.x, self.ts, context=ctx, fs=self.fs_b, x_concat=[z]))
         else:
-            v_c = self.unet(self.x, self.ts, context=self.ctx_c, fs=self.fs, x_concat=[self.z_c])
-            v_u = self.unet(self.x, self.ts, context=self.ctx_u, fs=self.fs, x_concat=[self.z_u]) if self.cfg else None
+            v_c = self.unet(self.x, self.ts, context=self.ctx_c, fs=self.fs_b, x_concat=[self.z_c])
+            v_u = self.unet(self.x, self.ts, context=self.ctx_u, fs=self.fs_b, x_concat=[self.z_u]) if self.cfg else None
         abi.ddim_cfg_step(self.x, v_c, v_u, self.noise, self.x, self.pred_x0, self.cfg_scale, self.rescale,
                           self.temperature, self.table, self.step_index, True, self.ws)
 
@@ -163,10 +201,8 @@ class GraphedCFGStep:
         self.step_index.zero_()
 
     def refresh_conditioning(self):
+        """The static context buffers were overwritten: recompute the cached K|V projections the graph reads."""
         if self.batched:
-            b = self.x.shape[0]
-            self.ctx_b[:b].copy_(self.ctx_c); self.ctx_b[b:].copy_(self.ctx_u)
-            self.z_b[:b].copy_(self.z_c); self.z_b[b:].copy_(self.z_u)
             self.unet.refresh_context(self.ctx_b, self.x.shape[2])
             return
         for ctx in (self.ctx_c, self.ctx_u):
@@ -319,7 +355,12 @@ class DDIMSampler(object):
                       precision=None, fs=None, guidance_rescale=0.0, **kwargs):
         device = self.model.betas.device
         b = shape[0]
-        img = torch.randn(shape, device=device) if x_T is None else x_T
+        if x_T is None:
+            # every rank of a CFG- / sequence-parallel replica group must start from the SAME latent: the draw of
+            # the group's first rank is broadcast, exactly like the per-step noise (ddim.py:150-153 draws once)
+            img = self._sync_noise(torch.randn(shape, device=device))
+        else:
+            img = x_T
         out_dtype = img.dtype
         if precision is not None:
             if precision == 16:
@@ -357,7 +398,9 @@ class DDIMSampler(object):
                 if callback:
                     callback(i)
                 if img_callback:
-                    img_callback(pred_x0.to(out_dtype), i)
+                    # the graph's static buffer is overwritten by the next replay: hand out a fresh tensor, as the
+                    # reference does every step
+                    img_callback(pred_x0.to(out_dtype, copy=True), i)
                 if index % log_every_t == 0 or index == total_steps - 1:
                     intermediates["x_inter"].append(img.to(out_dtype, copy=True))
                     intermediates["pred_x0"].append(pred_x0.to(out_dtype, copy=True))
@@ -398,9 +441,38 @@ class DDIMSampler(object):
         if not ok:
             return None
         table, _ = self._step_table(False)
+        # The capture is cached on the U-Net (a DDIMSampler is constructed per call, model.py:705): later calls
+        # with the same shapes and settings copy their conditioning into the static buffers and replay.
+        cfg = uc is not None and cfg_scale != 1.0
+        if not cfg:
+            uc = None
+        cache = unet._graph_cache
+        for g in cache:
+            if (g.sampler_key == self._graph_key() and g.signature()[:6] == (
+                    tuple(shape), cfg, float(cfg_scale), float(guidance_rescale), float(temperature), tuple(table.shape))):
+                try_sig = GraphedCFGStep._sources(cond, uc)
+                sig = lambda t: None if t is None else (tuple(t.shape), t.dtype)
+                if tuple(sig(t) for t in try_sig) == g.signature()[6:10] and (fs is None) == (g.fs_b is None):
+                    g.sampler = self
+                    g.load(cond, uc, fs, table)
+                    cache.remove(g)
+                    cache.append(g)
+                    return g
         g = GraphedCFGStep(self, unet, tuple(shape), cond, uc, fs, cfg_scale, guidance_rescale, temperature, table)
+        g.sampler_key = self._graph_key()
         g.capture()
+        cache.append(g)
+        while len(cache) > 2:
+            cache.pop(0)
         return g
+
+    def _graph_key(self):
+        """Sampler state a captured step depends on besides its tensor shapes."""
+        unet = self._native_unet()
+        p0 = next(unet.parameters())
+        return (self.batch_cfg, id(self.cfg_parallel) if self.cfg_parallel is not None else None,
+                id(unet.sequence_parallel) if unet.sequence_parallel is not None else None,
+                unet.compute_mode, unet.kernel_impl, p0.dtype, str(p0.device))
 
     def _sync_noise(self, noise):
         if self.replica_group is not None:
@@ -430,8 +502,8 @@ class DDIMSampler(object):
 
     def _can_batch_cfg(self, c, uc):
         unet = self._native_unet()
-        return (self.batch_cfg and unet is not None and unet.sequence_parallel is None
-                and isinstance(c, dict) and isinstance(uc, dict))
+        return (self.batch_cfg and unet is not None and isinstance(c, dict) and isinstance(uc, dict)
+                and (unet.sequence_parallel is None or getattr(unet.sequence_parallel, "batch_ok", False)))
 
     def _denoise_cfg_batched(self, x32, t, c, uc, **kwargs):
         """Both CFG branches as one forward over 2b samples (rows [0,b) cond, [b,2b) uncond).  The concatenated

@@ -160,7 +160,11 @@ class UNetModel(nn.Module):
                            resblock_updown=resblock_updown, tempspatial_aware=tempspatial_aware,
                            use_relative_position=use_relative_position, use_causal_attention=use_causal_attention,
                            image_cross_attention_scale_learnable=image_cross_attention_scale_learnable,
-                           conv_resample=not conv_resample, num_head_channels=num_head_channels != 64)
+                           conv_resample=not conv_resample, num_head_channels=num_head_channels != 64,
+                           # an option the reference would act on (temporal attn2 attending to the context) that this
+                           # path does not implement: reject it instead of silently computing something else.
+                           # (`dropout` is inert: this is an inference-only module, always in eval semantics.)
+                           temporal_selfatt_only=not temporal_selfatt_only)
         bad = [k for k, v in unsupported.items() if v]
         if bad:
             raise NotImplementedError(
@@ -235,19 +239,21 @@ class UNetModel(nn.Module):
         self._packs = {}          # (mode) -> {key: packed device tensor}
         self._ctx_cache = OrderedDict()
         self._freqs = None
+        self._graph_cache = []    # captured CFG steps (sampler.GraphedCFGStep), most recently used last
 
-    # ---- cache invalidation: any parameter move / reload drops the packed copies
+    # ---- cache invalidation: any parameter move / reload drops the packed copies (and the CUDA graphs that
+    # bake their addresses)
     def _apply(self, fn, *a, **k):
-        self._packs, self._ctx_cache, self._freqs = {}, OrderedDict(), None
+        self._packs, self._ctx_cache, self._freqs, self._graph_cache = {}, OrderedDict(), None, []
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packs, self._ctx_cache = {}, OrderedDict()
+        self._packs, self._ctx_cache, self._graph_cache = {}, OrderedDict(), []
         return super().load_state_dict(*a, **k)
 
     def invalidate_packed_weights(self):
         """Call after mutating parameters in place."""
-        self._packs, self._ctx_cache = {}, OrderedDict()
+        self._packs, self._ctx_cache, self._graph_cache = {}, OrderedDict(), []
 
     @torch.no_grad()
     def refresh_context(self, context, frames):
@@ -258,6 +264,8 @@ class UNetModel(nn.Module):
                 r = _Runner.__new__(_Runner)
                 r.m, r.context, r.dev = self, context, context.device
                 r.sp, r.Tf = self.sequence_parallel, frames
+                if hasattr(r.sp, "current"):
+                    r.sp = r.sp.current()
                 r.T = frames if r.sp is None else frames // r.sp.P
                 r.mode = key[4]
                 r.opdt = torch.bfloat16 if r.mode == "bf16" else torch.float32
@@ -323,13 +331,19 @@ class _Runner:
         self.sd = None
         self.b, _, self.T, self.H0, self.W0 = x.shape
         self.sp = model.sequence_parallel
+        if hasattr(self.sp, "current"):        # VirtualSequenceParallel hub -> the calling thread's rank view
+            self.sp = self.sp.current()
         self.Tf = self.T                       # frames of the clip; self.T = frames held by this rank
         if self.sp is not None:
-            if self.b != 1:
-                raise RuntimeError("sequence parallelism shards a single clip (batch 1)")
+            if self.b != 1 and not getattr(self.sp, "batch_ok", False):
+                raise RuntimeError("this sequence-parallel transport shards a single clip (batch 1)")
             down = 2 ** (len(model.channel_mult) - 1)
             self.sp.check(self.Tf, (self.H0 // down) * (self.W0 // down))
             self.T = self.Tf // self.sp.P
+            # the largest tensor that is ever re-sharded (trunk rows of one level, fp32)
+            elems = max(self.b * self.T * (self.H0 >> l) * (self.W0 >> l) * model.model_channels * mult
+                        for l, mult in enumerate(model.channel_mult))
+            self.sp.prepare(elems, 1, self.b, self.dev)
 
     # ---- buffers
     def new(self, rows, cols, dtype):
@@ -445,8 +459,7 @@ class _Runner:
         y = self.new(x.shape[0], x.shape[1], out_dtype or self.opdt)
         rows = x.shape[0] // n_inst
         if clip_wide and self.sp is not None:
-            abi.groupnorm_sp(x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu,
-                             self.sp.all_reduce_sum, rows * self.sp.P)
+            self.sp.groupnorm(abi, x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu)
         else:
             # statistics left behind by the producer(s) of x (both halves for a skip concatenation)
             cs, states = getattr(x, "_cs", None), getattr(x, "_cs_states", None)
@@ -499,22 +512,30 @@ class _Runner:
             skip = x
         else:
             skip = self.linear(x, p + "skip_connection.weight", p + "skip_connection.bias", torch.float32)
+        tconv_sp = blk.use_temporal_conv and self.sp is not None
         h = self.conv3x3(a, p + "out_layers.3.weight", p + "out_layers.3.bias", H, W, torch.float32, residual=skip,
-                         stats=True, out=None if blk.use_temporal_conv else out)
+                         stats=True, out=(self._send_slot(x.shape[0], blk.out_channels) if tconv_sp else
+                                          None if blk.use_temporal_conv else out))
         if blk.use_temporal_conv:
             q = p + "temopral_conv."
             hw = H * W
             if self.sp is not None:                 # frames -> pixels: every rank gets all T frames of hw/P pixels
-                h = self.sp.frames_to_pixels(h, self.T, hw)
+                h = self.sp.frames_to_pixels(h, self.b, self.T, hw)
                 hw //= self.sp.P
             y = h
             for i, ci in ((1, 2), (2, 3), (3, 3), (4, 3)):
                 a = self.gn(y, f"{q}conv{i}.0.", self.b, 1e-5, True, clip_wide=True)
+                last = i == 4
                 y = self.convt3(a, f"{q}conv{i}.{ci}.weight", f"{q}conv{i}.{ci}.bias", hw, torch.float32,
-                                residual=h if i == 4 else None, stats=True,
-                                out=out if (i == 4 and self.sp is None) else None)
-            h = y if self.sp is None else self.sp.pixels_to_frames(y, self.T, H * W)
+                                residual=h if last else None, stats=True,
+                                out=(out if self.sp is None else self._send_slot(h.shape[0], h.shape[1])) if last else None)
+            h = y if self.sp is None else self.sp.pixels_to_frames(y, self.b, self.T, H * W, out=out)
         return h
+
+    def _send_slot(self, rows, cols):
+        """Where the producer of the next frame<->pixel re-shard should write (the transport's peer-visible send
+        slot), or None when the transport takes any tensor."""
+        return self.sp.send_buffer(rows, cols, self.dev)
 
     def _attn(self, q, k, v, out, batch, heads, n_q, n_kv, accumulate=False):
         ok = False
@@ -599,7 +620,7 @@ class _Runner:
         p = mod._pfx
         HW, T = H * W, self.Tf
         if self.sp is not None:
-            x = self.sp.frames_to_pixels(x, self.T, HW)
+            x = self.sp.frames_to_pixels(x, self.b, self.T, HW)
             HW //= self.sp.P
         a = self.gn(x, p + "norm.", self.b, 1e-6, False, clip_wide=True)
         t = self.linear(a, p + "proj_in.weight", p + "proj_in.bias", torch.float32)
@@ -608,8 +629,8 @@ class _Runner:
                     o=lambda ld: (HW, T * HW * ld, ld, HW * ld))
         t = self._blocks(mod, t, mod.n_heads, addr, None)
         y = self.linear(t, p + "proj_out.weight", p + "proj_out.bias", torch.float32, residual=x, stats=True,
-                        out=out if self.sp is None else None)
-        return y if self.sp is None else self.sp.pixels_to_frames(y, self.T, H * W)
+                        out=out if self.sp is None else self._send_slot(x.shape[0], x.shape[1]))
+        return y if self.sp is None else self.sp.pixels_to_frames(y, self.b, self.T, H * W, out=out)
 
     # ---- conditioning -------------------------------------------------------------------------
     def _context_kv(self, reuse=None):
@@ -671,7 +692,7 @@ class _Runner:
         if reuse is not None:
             return out
         m._ctx_cache[key] = out
-        while len(m._ctx_cache) > 4:
+        while len(m._ctx_cache) > 8:
             m._ctx_cache.popitem(last=False)
         return out
 
@@ -722,6 +743,10 @@ class _Runner:
         last = len(seq) - 1
         for idx, layer in enumerate(seq):
             o = out if idx == last else None
+            if (self.sp is not None and idx < last and isinstance(seq[idx + 1], TemporalTransformer)
+                    and isinstance(layer, SpatialTransformer)):
+                # the next layer starts with a frames -> pixels re-shard: produce straight into the send slot
+                o = self._send_slot(h.shape[0], layer.in_channels)
             if isinstance(layer, ResBlock):
                 h = self.res_block(layer, h, H, W, out=o)
             elif isinstance(layer, SpatialTransformer):
@@ -804,7 +829,9 @@ class _Runner:
             cat._cs_states = [hv._cs_state, sv._cs_state]
             cats[k] = (cat, hv, sv)
             if i == 0 and m.addition_attention:
-                h, H, W = self.run_block(seq, h, H, W)
+                # init_attn is a TemporalTransformer: under sequence parallelism the stem writes into the send slot
+                o0 = None if self.sp is None else self._send_slot(h.shape[0], c_s)
+                h, H, W = self.run_block(seq, h, H, W, out=o0)
                 h, H, W = self.run_block(m.init_attn, h, H, W, out=sv)
             else:
                 h, H, W = self.run_block(seq, h, H, W, out=sv)

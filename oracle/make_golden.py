@@ -1,6 +1,7 @@
 """Generate tests/golden/*.npz by EXECUTING THE REFERENCE ITSELF (build container only).
 
     python oracle/make_golden.py            # writes tests/golden/, prints oracle-vs-reference errors
+    python oracle/make_golden.py --full     # the full-width (1.44 B parameter) fixture, ~15 min of CPU
 
 Imports the unmodified reference modules from /root/reference/DynamiCrafter (they need only
 torch/einops/numpy), builds structurally identical but narrow models (model_channels 64),
@@ -144,7 +145,61 @@ def sampler_case(name, params, dparams, latent, S, cfg_scale, rescale, seed_w, s
                              eta=eta, noise_seed=seed_x + 99)))
 
 
+def full_width_case(name="full512", seed_w=1234, seed_x=0, stride=8):
+    """The REAL configuration (inference_512_v1.0.yaml U-Net, 1.44 B parameters, latent 4x16x40x64, context 333x1024)
+    executed by the reference itself: one forward stored whole (fp32 and fp64), plus teacher-forced forwards at five
+    DDIM timesteps of the 50-step trailing schedule with the cond and the uncond context — x_t = q_sample(x0, t) with
+    the model's bf16 schedule buffers, so every timestep sees a latent of the right statistics — stored strided
+    (every `stride`-th element) to keep the fixture small.  Pins the oracle AND the GPU path at full width."""
+    params, latent = pcfg.UNET_512, pcfg.LATENT_512
+    ref = build_reference_unet(params, seed_w)
+    shapes = unet_oracle.unet_param_shapes(params)
+    sd2 = synth_state_dict(shapes, seed_w)
+    sd = ref.state_dict()
+    assert set(shapes) == set(sd) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+    inp = synth_inputs(1, latent, params["context_dim"], seed_x)
+    buf = ddim_oracle.model_schedule(**pcfg.DIFFUSION_512)
+    fs_t = torch.tensor([params["default_fs"]], dtype=torch.long)
+    out = {}
+    with torch.no_grad():
+        x = torch.cat([inp["x"], inp["c_concat"]], 1)
+        t = torch.tensor([499], dtype=torch.long)
+        y_ref = ref(x, t, context=inp["context"], fs=fs_t)
+        y_orc = unet_oracle.unet_forward(sd2, params, x, t, inp["context"], fs_t)
+        e = rel_l2(y_orc, y_ref)
+        print(f"[unet:{name}] t=499 oracle vs reference fp32 rel-L2 = {e:.3e}; out std = {float(y_ref.std()):.3f}", flush=True)
+        assert e < 2e-5, e
+        out["y"] = y_ref.numpy()
+        steps = [999, 759, 499, 259, 19]
+        x0 = inp["x"]
+        noise = synth_inputs(1, latent, params["context_dim"], seed_x + 11)["x"]
+        for tv in steps:
+            tt = torch.tensor([tv], dtype=torch.long)
+            xt = (buf["sqrt_alphas_cumprod"].float()[tv] * x0 + buf["sqrt_one_minus_alphas_cumprod"].float()[tv] * noise)
+            xc = torch.cat([xt, inp["c_concat"]], 1)
+            for tag, ctx in (("c", inp["context"]), ("u", inp["uc_context"])):
+                v = ref(xc, tt, context=ctx, fs=fs_t)
+                out[f"v_{tag}_{tv}"] = v.flatten()[::stride].numpy().copy()
+                if tv in (999, 19) and tag == "c":
+                    eo = rel_l2(unet_oracle.unet_forward(sd2, params, xc, tt, ctx, fs_t), v)
+                    print(f"[unet:{name}] t={tv} oracle vs reference rel-L2 = {eo:.3e}", flush=True)
+                    assert eo < 2e-5, eo
+            print(f"[unet:{name}] teacher-forced t={tv} done", flush=True)
+        y64 = ref.double()(x.double(), t, context=inp["context"].double(), fs=fs_t).float()
+        print(f"[unet:{name}] reference fp32 vs fp64 = {rel_l2(y_ref, y64):.3e}", flush=True)
+        out["y64"] = y64.numpy()
+    np.savez_compressed(
+        os.path.join(GOLD, f"unet_{name}.npz"), **out,
+        meta=json.dumps(dict(params=params, latent=list(latent), seed_w=seed_w, seed_x=seed_x, t=499,
+                             fs=params["default_fs"], steps=steps, stride=stride, noise_seed=seed_x + 11,
+                             dparams=pcfg.DIFFUSION_512, per_frame_image=True)))
+
+
 def main():
+    if "--full" in sys.argv:         # ~15 min of CPU: the full-width fixture only
+        os.makedirs(GOLD, exist_ok=True)
+        torch.set_num_threads(os.cpu_count())
+        return full_width_case()
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     small = pcfg.small_unet()

@@ -116,7 +116,23 @@ def _heads(x, h):
     return x.reshape(b, n, h, -1).permute(0, 2, 1, 3)  # b h n d
 
 
+#: score-matrix elements above which `_softmax_attn` walks the batch (frames) one sample at a time.  Same arithmetic
+#: (every sample's softmax is independent); it only bounds memory: at 576x1024 the reference's einsum path
+#: materialises (16 frames x 5 heads) x 9216 x 9216 fp32 = 27 GB (attention.py:103-120).
+ATTN_CHUNK_ELEMS = 1 << 29
+
+
+#: "einsum" = the path the reference takes without xformers (materialised scores, attention.py:101-125);
+#: "sdpa" = torch's fused attention as the stand-in for xformers.memory_efficient_attention (attention.py:175), used
+#: only by bench.py's torch-on-GPU baseline arm.
+ATTN_IMPL = "einsum"
+
+
 def _softmax_attn(q, k, v, scale):
+    if ATTN_IMPL == "sdpa":
+        return F.scaled_dot_product_attention(q, k, v, scale=scale)
+    if q.shape[0] > 1 and q.shape[0] * q.shape[1] * q.shape[2] * k.shape[2] > ATTN_CHUNK_ELEMS:
+        return torch.cat([_softmax_attn(q[i:i + 1], k[i:i + 1], v[i:i + 1], scale) for i in range(q.shape[0])], 0)
     sim = torch.matmul(q, k.transpose(-1, -2)) * scale
     return torch.matmul(sim.softmax(dim=-1), v)
 

@@ -49,15 +49,22 @@ def _reshard(rank, world):
     g = torch.Generator().manual_seed(0)
     full = torch.randn(T, HW, C, generator=g)                     # (t, p, c) of the whole clip
     sp = SequenceParallel()
+    assert sp.transport == "nccl"                                 # gloo group: the torch.distributed transport
     sp.check(T, HW)
     t0, t1 = sp.frame_range(T)
     mine = full[t0:t1].reshape(-1, C).contiguous()                # frame-sharded rows (t_local, p)
-    pix = sp.frames_to_pixels(mine, t1 - t0, HW)                  # -> (t, p_local)
+    pix = sp.frames_to_pixels(mine, 1, t1 - t0, HW)               # -> (t, p_local)
     hwl = HW // world
     want = full[:, rank * hwl:(rank + 1) * hwl].reshape(-1, C)
     ok1 = torch.equal(pix, want)
-    back = sp.pixels_to_frames(pix, t1 - t0, HW)
+    back = sp.pixels_to_frames(pix, 1, t1 - t0, HW)
     ok2 = torch.equal(back, mine)
+    # two samples in one exchange (cond | uncond batched): rows (b, t_local, p) <-> (b, t, p_local)
+    full2 = torch.stack([full, full.flip(0) * 2.0])               # (b, t, p, c)
+    mine2 = full2[:, t0:t1].reshape(-1, C).contiguous()
+    pix2 = sp.frames_to_pixels(mine2, 2, t1 - t0, HW)
+    ok1 = ok1 and torch.equal(pix2, full2[:, :, rank * hwl:(rank + 1) * hwl].reshape(-1, C))
+    ok2 = ok2 and torch.equal(sp.pixels_to_frames(pix2, 2, t1 - t0, HW), mine2)
     # clip-wide GroupNorm statistics from per-rank partial sums == statistics of the whole tensor
     G = 4
     x = pix.double().reshape(-1, G, C // G)

@@ -41,6 +41,19 @@ def test_unet_oracle_matches_reference_golden(name):
     assert rel_l2(y, z["y64"]) < 2e-5
 
 
+def test_unet_oracle_matches_full_width_reference_golden():
+    """The REAL configuration (1.44 B parameters, latent 4x16x40x64, context 333x1024): the oracle against the forward
+    the reference itself computed in the build container (`oracle/make_golden.py --full`)."""
+    from pandora_b200.config import UNET_512
+    z, meta = load_golden("unet_full512")
+    assert meta["params"] == UNET_512
+    sd = synth_state_dict(unet_oracle.unet_param_shapes(UNET_512), meta["seed_w"])
+    x, t, ctx, fs = unet_case_inputs(meta)
+    y = unet_oracle.unet_forward(sd, UNET_512, x, t, ctx, fs)
+    assert rel_l2(y, z["y"]) < 2e-5
+    assert rel_l2(y, z["y64"]) < 2e-5
+
+
 def test_param_inventory_full_size():
     from pandora_b200.config import UNET_512
     shapes = unet_oracle.unet_param_shapes(UNET_512)

@@ -37,12 +37,16 @@ def _worker(rank, world, port, mode, ret):
     try:
         from pandora_b200 import DDIMSampler, LatentDiffusionLite, config
         from pandora_b200.dist import CFGParallel, SequenceParallel
-        dtype = torch.bfloat16 if mode.endswith("bf16") else torch.float32
+        parts = mode.split("-")
+        dtype = torch.bfloat16 if "bf16" in parts else torch.float32
+        transport = "nccl" if "nccl" in parts else "p2p"
         p, m, inp = _build(dtype)
         t = torch.tensor([499], device="cuda")
         if mode.startswith("unet"):
-            m.sequence_parallel = SequenceParallel()
+            m.sequence_parallel = SequenceParallel(transport=transport)
             y = m(inp["x"], t, context=inp["context"], x_concat=[inp["c_concat"]])
+            y2 = m(inp["x"], t, context=inp["context"], x_concat=[inp["c_concat"]])      # slots / epochs reused
+            assert torch.equal(y, y2)
             ret[rank] = y.float().cpu()
         else:
             model = LatentDiffusionLite(m, **config.DIFFUSION_512).cuda()
@@ -50,15 +54,15 @@ def _worker(rank, world, port, mode, ret):
             if mode.startswith("cfg"):
                 s.cfg_parallel = CFGParallel()
             else:
-                m.sequence_parallel = SequenceParallel()
+                m.sequence_parallel = SequenceParallel(transport=transport)
             s.replica_group = dist.group.WORLD
-            s.use_cuda_graph = mode.split("-")[1] == "graph"
+            s.use_cuda_graph = "graph" in parts
             cond = dict(c_crossattn=[inp["context"]], c_concat=[inp["c_concat"]])
             uc = dict(c_crossattn=[inp["uc_context"]], c_concat=[inp["c_concat"]])
             torch.manual_seed(100 + rank)         # different seeds: the broadcast must make the noise identical
             x, _ = s.sample(S=4, batch_size=1, shape=(4, 16, 16, 16), conditioning=cond, unconditional_conditioning=uc,
-                            unconditional_guidance_scale=7.5, eta=1.0, x_T=inp["x"], verbose=False,
-                            timestep_spacing="uniform_trailing", guidance_rescale=0.7)
+                            unconditional_guidance_scale=7.5, eta=1.0, x_T=None if "noxT" in parts else inp["x"],
+                            verbose=False, timestep_spacing="uniform_trailing", guidance_rescale=0.7)
             ret[rank] = x.float().cpu()
     finally:
         dist.destroy_process_group()
@@ -72,18 +76,22 @@ def _run(mode, world=2):
     return [ret[r] for r in range(world)]
 
 
-@pytest.mark.parametrize("mode,tol", [("unet-fp32", 1e-4), ("unet-bf16", 2e-2)])
+@pytest.mark.parametrize("mode,tol", [("unet-fp32-p2p", 1e-4), ("unet-bf16-p2p", 2e-2), ("unet-fp32-nccl", 1e-4),
+                                      ("unet-bf16-nccl", 2e-2)])
 def test_sequence_parallel_unet_matches_single_gpu(mode, tol):
     outs = _run(mode)
-    dtype = torch.bfloat16 if mode.endswith("bf16") else torch.float32
+    dtype = torch.bfloat16 if "bf16" in mode else torch.float32
     p, m, inp = _build(dtype)
     ref = m(inp["x"], torch.tensor([499], device="cuda"), context=inp["context"], x_concat=[inp["c_concat"]]).float().cpu()
     assert torch.equal(outs[0], outs[1])
     assert rel_l2(outs[0], ref) < tol
 
 
-@pytest.mark.parametrize("mode", ["cfg-eager-fp32", "cfg-graph-fp32", "sp-eager-fp32", "sp-graph-fp32"])
+@pytest.mark.parametrize("mode", ["cfg-eager-fp32", "cfg-graph-fp32", "sp-eager-fp32-p2p", "sp-graph-fp32-p2p",
+                                  "sp-eager-fp32-nccl", "sp-graph-fp32-nccl", "sp-graph-fp32-p2p-noxT", "cfg-graph-fp32-noxT"])
 def test_parallel_sampler_matches_single_gpu(mode):
+    """`noxT`: x_T is drawn inside sample() with a different seed on every rank; the replica-group broadcast must make
+    the ranks start from rank 0's latent (they would otherwise denoise different clips and disagree)."""
     outs = _run(mode)
     from pandora_b200 import DDIMSampler, LatentDiffusionLite, config
     p, m, inp = _build(torch.float32)
@@ -92,7 +100,7 @@ def test_parallel_sampler_matches_single_gpu(mode):
     uc = dict(c_crossattn=[inp["uc_context"]], c_concat=[inp["c_concat"]])
     torch.manual_seed(100)                        # rank 0's seed: its noise is what gets broadcast
     ref, _ = s.sample(S=4, batch_size=1, shape=(4, 16, 16, 16), conditioning=cond, unconditional_conditioning=uc,
-                      unconditional_guidance_scale=7.5, eta=1.0, x_T=inp["x"], verbose=False,
+                      unconditional_guidance_scale=7.5, eta=1.0, x_T=None if "noxT" in mode else inp["x"], verbose=False,
                       timestep_spacing="uniform_trailing", guidance_rescale=0.7)
     assert torch.equal(outs[0], outs[1])
     assert rel_l2(outs[0], ref.float().cpu()) < 1e-4

@@ -114,7 +114,9 @@ def test_tc_gemm_back_to_back_launches_are_deterministic(abi):
 
 # ------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,heads,nq,nk", [(2, 2, 128, 128), (3, 5, 160, 160), (2, 1, 640, 640), (1, 2, 2560, 2560),
-                                           (2, 3, 200, 77), (2, 2, 64, 16), (1, 1, 300, 129)])
+                                           (2, 3, 200, 77), (2, 2, 64, 16), (1, 1, 300, 129),
+                                           # the spatial token counts of the 576x1024 clip (72x128 ... 9x16 latents)
+                                           (1, 1, 9216, 9216), (1, 2, 2304, 2304), (2, 2, 576, 576), (2, 3, 144, 144)])
 def test_tc_attention_frame_batched(abi, B, heads, nq, nk):
     C = heads * 64
     qkv = rnd(B * nq, 3 * C, seed=30, dtype=BF)
@@ -136,6 +138,23 @@ def test_tc_attention_frame_batched(abi, B, heads, nq, nk):
     assert e < 6e-3, e
     assert abi.attention(qop, kop, vop, out, (1, nq * C, 0, C), B, heads, nq, nk, 0.125, abi.BF16, accumulate=True, tc=True)
     assert rel_l2(out, 2 * ref) < 1e-2
+
+
+@pytest.mark.parametrize("n,ramp", [(9216, (0.05, 8.0)), (2560, (8.0, 0.05)), (2304, (0.02, 12.0))])
+def test_tc_attention_online_softmax_with_drifting_maxima(abi, n, ramp):
+    """Key norms ramp over the sequence, so the row maxima drift by tens of log2 units across the key tiles: the
+    accumulator in tensor memory is rescaled lazily (only when a maximum grows by more than 2^8) and stale maxima
+    are used in between; an un-normalised P reaches 2^8 there.  Both directions, 18 .. 72 key tiles."""
+    heads, C = 1, 64
+    q = rnd(n, C, seed=41, dtype=BF)
+    k = (rnd(n, C, seed=42) * torch.linspace(ramp[0], ramp[1], n, device="cuda")[:, None]).to(BF)
+    v = rnd(n, C, seed=43, dtype=BF)
+    out = torch.full((n, C), float("nan"), dtype=BF, device="cuda")
+    op = lambda t: abi.operand(t, 1, n * C, 0, C, 0)
+    assert abi.attention(op(q), op(k), op(v), out, (1, n * C, 0, C), 1, heads, n, n, 0.125, abi.BF16, tc=True)
+    ref = ref_attn(q[None], k[None], v[None], heads)[0]
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 8e-3
 
 
 def test_tc_attention_text_kv_shared_across_frames(abi):

@@ -54,6 +54,41 @@ def attn(n, heads):
     abi.attention(op(0), op(C), op(2 * C), o, (1, n * C, 0, C), B, heads, n, n, 0.125, abi.BF16, False, tc=True)
 
 
+def xattn(n, heads, T=16):
+    """text+image cross-attention as the U-Net runs it: 93 keys per frame, two softmax segments"""
+    C = heads * 64
+    q = rn(B * n, C)
+    kv = rn(B * 93, 2 * C)
+    o = torch.empty(B * n, C, device=dev, dtype=BF)
+    k_op = abi.operand(kv, 1, 93 * 2 * C, 0, 2 * C, 0)
+    v_op = abi.operand(kv, 1, 93 * 2 * C, 0, 2 * C, C)
+    abi.attention(abi.operand(q, 1, n * C, 0, C, 0), k_op, v_op, o, (1, n * C, 0, C), B, heads, n, 93, 0.125,
+                  abi.BF16, False, tc=True, kv_split=77)
+
+
+def tattn(hw, heads, T=16):
+    C = heads * 64
+    qkv = rn(2 * T * hw, 3 * C)
+    o = torch.empty(2 * T * hw, C, device=dev, dtype=BF)
+    ld = 3 * C
+    op = lambda off: abi.operand(qkv, hw, T * hw * ld, ld, hw * ld, off)
+    abi.attention(op(0), op(C), op(2 * C), o, (hw, T * hw * C, C, hw * C), 2 * hw, heads, T, T, 0.125, abi.BF16)
+
+
+def gn(rows_per_inst, n_inst, C, fused=True):
+    M = rows_per_inst * n_inst
+    x = rf(M, C)
+    y = torch.empty(M, C, device=dev, dtype=BF)
+    cs = rf(M // 32, 2 * C) if fused else None
+    abi.groupnorm(x, y, n_inst, rows_per_inst, rf(C), rf(C), 1e-5, True, colstats=cs)
+
+
+def ln(M, C):
+    x = rf(M, C)
+    y = torch.empty(M, C, device=dev, dtype=BF)
+    abi.layernorm(x, y, rf(C), rf(C))
+
+
 for rep in range(2):                      # first round warms up (ncu: use --launch-skip to drop it)
     if want("conv"):
         conv(320, 320, 40, 64)            # 1: level-0 ResBlock conv
@@ -73,5 +108,17 @@ for rep in range(2):                      # first round warms up (ncu: use --lau
     if want("attn"):
         attn(2560, 5)                     # 13
         attn(640, 10)                     # 14
+    if want("xattn"):
+        xattn(2560, 5)                    # 15: cross-attention level 0
+        xattn(640, 10)                    # 16
+        xattn(160, 20)                    # 17
+    if want("tattn"):
+        tattn(2560, 5)                    # 18: temporal attention level 0
+    if want("norm"):
+        gn(2560, 32, 320)                 # 19: per-frame GN, fused stats (2 launches)
+        gn(40960, 2, 320)                 # 20: clip-wide GN, fused stats
+        gn(640, 2, 1280, fused=False)     # 21: small level, 3 launches
+        ln(81920, 320)                    # 22
+        ln(5120, 1280)                    # 23
     torch.cuda.synchronize()
 print("done")
