@@ -77,7 +77,7 @@ typedef struct pb_gemm_args {
      pb_tc_gemm_workspace_bytes(); NULL or too small => no split (results identical up to fp32 summation order) */
   void* workspace;
   int64_t workspace_bytes;
-  /* optional (pb_tc_gemm, fp32 output): per-column (sum, sumsq) of the stored values over every 32-row slab of
+  /* optional (pb_tc_gemm; of the ROUNDED values for a bf16 output): per-column (sum, sumsq) of the stored values over every 32-row slab of
      the output, colstats[(m / 32) * ld_colstats + 2 * n + {0, 1}] (ld_colstats in floats, >= 2 * N_out).  This is
      the first pass of the GroupNorm that consumes the output (openaimodel3d.py:155,179,259-268; attention.py:265,331)
      fused into the producer; pb_groupnorm_stats_cols folds it.  Written only when pb_tc_gemm_colstats_ok() says so

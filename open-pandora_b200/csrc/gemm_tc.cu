@@ -296,10 +296,11 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
       // ---- (4) one bulk tensor store per chunk; prefetch the residual of this team's next chunk
       fence_proxy_async();
       team_bar_sync(team);
-      // ---- (4b) GroupNorm column statistics of the tile just staged (fp32 output only): warp w of the team
-      // owns the 32-row slab w, lane = column; rows of a swizzled slot are read conflict-free.  The bulk store
-      // reads the slot concurrently; the slot is not rewritten before this team's next barrier.
-      if (!OUT_BF16 && p.colstats != nullptr) {
+      // ---- (4b) GroupNorm column statistics of the tile just staged: warp w of the team owns the 32-row slab w,
+      // lane = column; rows of a swizzled slot are read conflict-free.  The bulk store reads the slot concurrently;
+      // the slot is not rewritten before this team's next barrier.  For a bf16 output the statistics are those of
+      // the ROUNDED values (what the norm that consumes the tensor will actually see).
+      if (p.colstats != nullptr) {
         const int w4 = (warp - 2) & 3;
         const int64_t m0 = out_row<MODE>(p, m_tile, w4 * 32);
         float cs_s = 0.f, cs_q = 0.f;
@@ -307,8 +308,15 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
         for (int i = 0; i < 32; ++i) {
           const int row = w4 * 32 + i;
           float t;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t)
-                       : "r"(sbuf + (uint32_t)(row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2))));
+          if (OUT_BF16) {
+            unsigned short h;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h)
+                         : "r"(sbuf + (uint32_t)(row * 64 + ((((lane >> 3) ^ ((row >> 1) & 3))) << 4) + ((lane & 7) << 1))));
+            t = __uint_as_float((uint32_t)h << 16);
+          } else {
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t)
+                         : "r"(sbuf + (uint32_t)(row * 128 + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2))));
+          }
           cs_s += t;
           cs_q = fmaf(t, t, cs_q);
         }
@@ -1099,7 +1107,8 @@ static int tc_plan(const pb_gemm_args* a, TcPlan* pl) {
     }
   }
   // fused GroupNorm column statistics: fp32 output written by this kernel itself, slabs aligned in row space
-  pl->colstats = a->colstats != nullptr && a->c_dtype == PB_F32 && p.splits == 1 && !geglu && slab_ok &&
+  pl->colstats = a->colstats != nullptr && p.splits == 1 && !geglu && slab_ok &&
+                 !(a->c_dtype == PB_BF16 && (a->epilogue & PB_EPI_RESIDUAL)) &&   // (that staging slot is fp32-shaped)
                  a->ld_colstats >= 2 * (int64_t)n_cols && a->ld_colstats % 2 == 0 &&
                  (reinterpret_cast<uintptr_t>(a->colstats) & 7) == 0;
   if (pl->colstats) { p.colstats = a->colstats; p.ld_cs = a->ld_colstats; }

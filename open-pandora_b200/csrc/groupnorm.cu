@@ -319,13 +319,25 @@ struct GnFold {
   float eps;
 };
 
+// Apply pass.  A CTA owns `rows_per_cta` consecutive rows of one instance and walks them as ONE flat stream of 4-channel
+// vectors (thread t takes vectors t, t + 256, ...: every thread busy for any channel count, neighbouring threads on
+// neighbouring 16-byte words), 4 loads in flight per thread.  The per-channel affine (scale, shift) is built once per CTA
+// in shared memory — from the folded fp64 partials when `fold.part` is set — and read back as float4 pairs; the row /
+// column of a vector is advanced incrementally (no integer division in the loop).  CTAs are sized by the host so that a
+// launch is a few waves of fat CTAs: the earlier version's 24-row CTAs spent as long in their prologue (fold, sqrt,
+// gamma / beta loads) as in streaming their 30 KB, and ran at 47 % of the DRAM rate.
 template <typename TX_, typename TY_>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int64_t R, int C,
-                const float* __restrict__ scale_shift, int silu, int TX, int TY, int rows_per_cta, GnFold fold) {
+                const float* __restrict__ scale_shift, int silu, int rows_per_cta, GnFold fold) {
+  extern __shared__ float4 gn_ab[];               // [cv] scale vectors, then [cv] shift vectors
   __shared__ float g_mean[32], g_rstd[32];
   const int inst = blockIdx.y;
   const int cv = C >> 2;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
+  const int nrows = (int)(r_begin + rows_per_cta < R ? rows_per_cta : R - r_begin);
+  const TX_* xb = x + ((int64_t)inst * R + r_begin) * ldx;
+  TY_* yb = y + ((int64_t)inst * R + r_begin) * ldy;
   if (fold.part != nullptr) {
     if (threadIdx.x < fold.G) {
       const double* pp = fold.part + ((int64_t)inst * fold.G + threadIdx.x) * fold.splits * 2;
@@ -338,55 +350,66 @@ gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int
       g_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)fold.eps));
     }
     __syncthreads();
-  }
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  if (ty >= TY) return;
-  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_cta;
-  const int64_t r_end = r_begin + rows_per_cta < R ? r_begin + rows_per_cta : R;
-  const float* sc = scale_shift + (int64_t)inst * 2 * C;
-  const TX_* xb = x + (int64_t)inst * R * ldx;
-  TY_* yb = y + (int64_t)inst * R * ldy;
-  for (int v = tx; v < cv; v += TX) {
-    float a[4], b[4];
-    if (fold.part != nullptr) {
-      const int cpg = C / fold.G;
+    const int cpg = C / fold.G;
+    for (int v = threadIdx.x; v < cv; v += GN_THREADS) {
+      float a[4], b[4], gm[4], bt[4];
+      load4(fold.gamma + v * 4, gm);
+      load4(fold.beta + v * 4, bt);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int c = v * 4 + j, g = c / cpg;
-        a[j] = g_rstd[g] * fold.gamma[c];
-        b[j] = fold.beta[c] - g_mean[g] * a[j];
+        const int g = (v * 4 + j) / cpg;
+        a[j] = g_rstd[g] * gm[j];
+        b[j] = bt[j] - g_mean[g] * a[j];
       }
-    } else {
-      load4(sc + v * 4, a);
-      load4(sc + C + v * 4, b);
+      gn_ab[v] = make_float4(a[0], a[1], a[2], a[3]);
+      gn_ab[cv + v] = make_float4(b[0], b[1], b[2], b[3]);
     }
-    int64_t r = r_begin + ty;
-    for (; r + 3 * TY < r_end; r += 4 * TY) {         // 4 independent 16-byte loads in flight per thread
-      float t[4][4];
+  } else {
+    const float* sc = scale_shift + (int64_t)inst * 2 * C;
+    for (int v = threadIdx.x; v < cv; v += GN_THREADS) {
+      gn_ab[v] = *reinterpret_cast<const float4*>(sc + v * 4);
+      gn_ab[cv + v] = *reinterpret_cast<const float4*>(sc + C + v * 4);
+    }
+  }
+  __syncthreads();
+  const int total = nrows * cv;
+  const int drow = GN_THREADS / cv, dcol = GN_THREADS - drow * cv;      // one step of 256 vectors in (row, column)
+  int row = (int)threadIdx.x / cv, col = (int)threadIdx.x - row * cv;
+  for (int i = threadIdx.x; i < total; i += 4 * GN_THREADS) {
+    float t[4][4];
+    int rr[4], cc[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) load4(xb + (r + u * TY) * ldx + (int64_t)v * 4, t[u]);
+    for (int u = 0; u < 4; ++u) {
+      rr[u] = row; cc[u] = col;
+      if (i + u * GN_THREADS < total) load4(xb + (int64_t)row * ldx + col * 4, t[u]);
+      row += drow; col += dcol;
+      if (col >= cv) { col -= cv; ++row; }
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 4; ++u) {
+      if (i + u * GN_THREADS < total) {
+        const float4 a = gn_ab[cc[u]], b = gn_ab[cv + cc[u]];
         float o[4];
+        o[0] = fmaf(t[u][0], a.x, b.x); o[1] = fmaf(t[u][1], a.y, b.y);
+        o[2] = fmaf(t[u][2], a.z, b.z); o[3] = fmaf(t[u][3], a.w, b.w);
+        if (silu) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float y0 = fmaf(t[u][j], a[j], b[j]);
-          o[j] = silu ? silu_f(y0) : y0;
+          for (int j = 0; j < 4; ++j) o[j] = silu_f(o[j]);
         }
-        store4(yb + (r + u * TY) * ldy + (int64_t)v * 4, o);
+        store4(yb + (int64_t)rr[u] * ldy + cc[u] * 4, o);
       }
-    }
-    for (; r < r_end; r += TY) {
-      float t[4], o[4];
-      load4(xb + r * ldx + (int64_t)v * 4, t);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float u = fmaf(t[j], a[j], b[j]);
-        o[j] = silu ? silu_f(u) : u;
-      }
-      store4(yb + r * ldy + (int64_t)v * 4, o);
     }
   }
+}
+
+// rows per CTA of the apply pass: ~6 CTAs per SM over the whole launch, at least 16 rows, at most what int32 indexing holds
+static inline int gn_apply_rows(int64_t n_inst, int64_t R, int64_t C) {
+  int64_t rows = ceil_div(n_inst * R, (int64_t)148 * 6);
+  if (rows < 16) rows = 16;
+  if (rows > R) rows = R;
+  const int64_t cap = ((int64_t)1 << 30) / (C / 4);
+  if (rows > cap) rows = cap;
+  return (int)rows;
 }
 
 }  // namespace pb
@@ -479,18 +502,17 @@ int pb_groupnorm_apply_cols(const void* x, int32_t x_dtype, int64_t ldx, void* y
   gn_cols_partial_kernel<<<pgrid, 256, 0, st>>>(colstats, ld_colstats, (int)C, groups, rows_per_inst, splits,
                                                 reinterpret_cast<double*>(ws));
   PB_LAUNCH_CHECK("gn_cols_partial_kernel");
-  int TX, TY;
-  gn_shape((int)(C / 4), &TX, &TY);
-  const int rows_per_cta = 8 * TY;
+  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C);
   dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
+  const size_t smem = (size_t)C * 2 * sizeof(float);
   GnFold fold;
   fold.part = reinterpret_cast<const double*>(ws); fold.gamma = gamma; fold.beta = beta;
   fold.splits = splits; fold.G = groups; fold.count = (double)rows_per_inst * (double)(C / groups); fold.eps = eps;
   PB_DISPATCH_DTYPE(x_dtype, TXT, {
     PB_DISPATCH_DTYPE(y_dtype, TYT, {
-      gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const TXT*>(x), ldx,
-                                                             reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
-                                                             nullptr, silu, TX, TY, rows_per_cta, fold);
+      gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, smem, st>>>(reinterpret_cast<const TXT*>(x), ldx,
+                                                                reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
+                                                                nullptr, silu, rows_per_cta, fold);
     })
   })
   PB_LAUNCH_CHECK("gn_apply_kernel");
@@ -544,18 +566,18 @@ int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int
   PB_REQUIRE(x && y && scale_shift, "pb_groupnorm_apply: null pointer");
   PB_REQUIRE(n_inst > 0 && n_inst <= 65535 && rows_per_inst > 0 && C > 0, "pb_groupnorm_apply: bad sizes");
   PB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "pb_groupnorm_apply: need C %% 4 == 0, ld %% 4 == 0");
+  PB_REQUIRE(C <= GN_MAX_C, "pb_groupnorm_apply: C <= %d supported", GN_MAX_C);
   cudaStream_t st = to_stream(stream);
-  int TX, TY;
-  gn_shape((int)(C / 4), &TX, &TY);
-  const int rows_per_cta = 8 * TY;
+  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C);
   dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
+  const size_t smem = (size_t)C * 2 * sizeof(float);
   PB_DISPATCH_DTYPE(x_dtype, TXT, {
     PB_DISPATCH_DTYPE(y_dtype, TYT, {
       GnFold nofold;
       memset(&nofold, 0, sizeof(nofold));
-      gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, 0, st>>>(reinterpret_cast<const TXT*>(x), ldx,
-                                                             reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
-                                                             scale_shift, silu, TX, TY, rows_per_cta, nofold);
+      gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, smem, st>>>(reinterpret_cast<const TXT*>(x), ldx,
+                                                                reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
+                                                                scale_shift, silu, rows_per_cta, nofold);
     })
   })
   PB_LAUNCH_CHECK("gn_apply_kernel");

@@ -20,6 +20,8 @@ Reference quirks kept on purpose: no clamp on 1 - a_prev - sigma^2 (NaN for some
 eta=1, e.g. S=6/10/25 with bf16 schedules), `uniform` spacing NaN on the last step, noise drawn even
 when sigma = 0.
 """
+import gc
+
 import numpy as np
 import torch
 
@@ -195,8 +197,18 @@ class GraphedCFGStep:
         self._keep = list(self.unet._ctx_cache.values())
         l0 = abi.launches
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        # A CUDAGraph that is destroyed while this stream is capturing invalidates the capture.  Captured steps of
+        # dropped models sit in reference cycles (model -> cache -> step -> model), so collect them NOW and keep
+        # the collector off until the capture has ended.
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph):
+                self._body()
+        finally:
+            if gc_was_on:
+                gc.enable()
         self.launches_per_step = abi.launches - l0
         self.step_index.zero_()
 

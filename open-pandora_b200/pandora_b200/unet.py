@@ -186,6 +186,11 @@ class UNetModel(nn.Module):
         self.compute_mode = None
         #: "auto" uses the tcgen05 kernels whenever they accept the shape (bf16 mode), "simt" never.
         self.kernel_impl = "auto"
+        #: bf16 mode: tensors whose ONLY consumer is a GroupNorm (the first conv of a ResBlock, the first three convs
+        #: of a TemporalConvBlock; openaimodel3d.py:157->179, 258-268) are stored in bf16 instead of fp32: they are not
+        #: part of the residual trunk, the norm's statistics come from the producer's epilogue, and the norm reads
+        #: 2 bytes per element instead of 4.  False = every GEMM output that feeds a norm stays fp32.
+        self.bf16_norm_inputs = True
         #: a `pandora_b200.dist.SequenceParallel` to run ONE clip across its ranks (frames sharded for the
         #: per-frame layers, pixels for the temporal layers); None = single GPU.  Batch must be 1.
         self.sequence_parallel = None
@@ -349,11 +354,11 @@ class _Runner:
     def new(self, rows, cols, dtype):
         return torch.empty((rows, cols), dtype=dtype, device=self.dev)
 
-    def new_trunk(self, rows, cols):
-        """fp32 rows that a GroupNorm may read next.  On the tcgen05 path they carry a column-statistics buffer
+    def new_trunk(self, rows, cols, dtype=torch.float32):
+        """Rows that a GroupNorm may read next.  On the tcgen05 path they carry a column-statistics buffer
         (`_cs`, [rows/32, 2*cols]) that the producing GEMM's epilogue fills, so the norm needs no pass over the
         tensor for its statistics (pb_gemm_args.colstats)."""
-        t = self.new(rows, cols, torch.float32)
+        t = self.new(rows, cols, dtype)
         t._cs = self.new(rows // 32, 2 * cols, torch.float32) if (self.use_tc and rows % 32 == 0) else None
         # validity flags live in plain dicts: a tensor attribute that refers back to the tensor or to one of its
         # views forms a reference cycle through the C++ side that the garbage collector cannot break (a leak)
@@ -418,8 +423,8 @@ class _Runner:
         M = kw.pop("M", a.shape[0])
         if out is not None:
             c = out
-        elif stats and out_dtype == torch.float32:
-            c = self.new_trunk(M, out_cols)
+        elif stats:
+            c = self.new_trunk(M, out_cols, out_dtype)
         else:
             c = self.new(M, out_cols, out_dtype)
         done = 0
@@ -505,7 +510,9 @@ class _Runner:
         rows_per_sample = self.T * H * W
         a = self.gn(x, p + "in_layers.0.", self.b * self.T, 1e-5, True)
         off, n = self.emb_slices[p]
-        h = self.conv3x3(a, p + "in_layers.2.weight", p + "in_layers.2.bias", H, W, torch.float32,
+        # tensors that only feed a GroupNorm (see UNetModel.bf16_norm_inputs)
+        mid_dt = self.opdt if (self.use_tc and self.m.bf16_norm_inputs) else torch.float32
+        h = self.conv3x3(a, p + "in_layers.2.weight", p + "in_layers.2.bias", H, W, mid_dt,
                          rowbias=self.emb_all[:, off:off + n], rowbias_rows=rows_per_sample, stats=True)
         a = self.gn(h, p + "out_layers.0.", self.b * self.T, 1e-5, True)
         if isinstance(blk.skip_connection, nn.Identity):
@@ -526,8 +533,8 @@ class _Runner:
             for i, ci in ((1, 2), (2, 3), (3, 3), (4, 3)):
                 a = self.gn(y, f"{q}conv{i}.0.", self.b, 1e-5, True, clip_wide=True)
                 last = i == 4
-                y = self.convt3(a, f"{q}conv{i}.{ci}.weight", f"{q}conv{i}.{ci}.bias", hw, torch.float32,
-                                residual=h if last else None, stats=True,
+                y = self.convt3(a, f"{q}conv{i}.{ci}.weight", f"{q}conv{i}.{ci}.bias", hw,
+                                torch.float32 if last else mid_dt, residual=h if last else None, stats=True,
                                 out=(out if self.sp is None else self._send_slot(h.shape[0], h.shape[1])) if last else None)
             h = y if self.sp is None else self.sp.pixels_to_frames(y, self.b, self.T, H * W, out=out)
         return h
