@@ -69,7 +69,6 @@ struct TcParams {
   int geglu_half;        // N / 2 when GEGLU
   int slot_bytes;        // epilogue staging slot size
   int epi_slots;         // staging slots per epilogue team (2, or 1 for long-K tiles: the bytes go to the TMA ring)
-  int pf_dist;           // L2 prefetch distance of the A operand in k-iterations (0 = off)
   // brick geometry (conv modes)
   int bw, bh, bn_img;    // CONV3X3: brick x, y, images ; CONVT3: bw = pixels, bh = frames
   int W, H;              // CONV3X3: image size ; CONVT3: W = HW (pixels per frame), H = T
@@ -79,10 +78,6 @@ struct TcParams {
   int splits;            // split-K ways (1 = off); split s covers k-iterations [s*kps, (s+1)*kps)
   int kps;               // k-iterations per split
   int pair;              // 1 = CTA-pair kernel (cta_group::2): block_n is the width of the 256-row pair tile
-  int mc;                // pairs per cluster (1, 2 or 4): the pairs of a cluster work on the SAME 256 rows and on mc
-                         // consecutive n-tiles; every CTA loads 1/mc of its A tile and multicasts it to the CTAs
-                         // that hold the same rows, so A crosses the L2 -> SM fabric once per cluster, not per pair
-  int sl_d1[4], sl_d2[4], sl_d3[4];   // coordinate offsets of A slice q inside the tile (dims 1..3 of the A map)
 };
 
 template <int MODE>
@@ -96,16 +91,6 @@ __device__ __forceinline__ int64_t out_row(const TcParams& p, int m_tile, int r)
   const int bi = r / (p.bw * p.bh);
   // CONV3X3: ((img*H + y)*W + x) ; CONVT3 (bn_img = 1): ((b*T + t)*HW + pix)
   return ((int64_t)(tn * p.bn_img + bi) * p.H + (ty * p.bh + by)) * p.W + (tx * p.bw + bx);
-}
-
-// ---- L2 prefetch of a tensor box (no shared memory, no barrier): hides the DRAM latency of first-touch A tiles
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 // ---- bulk tensor store / group management (epilogue)
@@ -155,7 +140,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 template <int MODE, bool GEGLU, typename TC, bool PAIR>
 __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUtensorMap* tmR, const TcParams& p,
                                               uint32_t tmem_base, uint32_t epi_base, uint32_t tfull0, uint32_t tempty0,
-                                              uint32_t rfull0, int first, int step, int total, int rank, int q_pair) {
+                                              uint32_t rfull0, int first, int step, int total, int rank) {
   constexpr int NT = num_teams(GEGLU);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int team = (warp - 2) >> 2;
@@ -174,10 +159,9 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
   // (work, chunk) -> tensor coordinates of the 128 x 32 output box
   auto coords = [&](int work, int ci, int (&c)[4], int& m_tile, int& n_tile) {
     int split = 0;
-    if (PAIR) {          // work = (pair m-tile, group of mc n-tiles); this pair owns n-tile q_pair of the group
-      const int n_groups = p.n_tiles / p.mc;
-      n_tile = (work % n_groups) * p.mc + q_pair;
-      m_tile = 2 * (work / n_groups) + rank;
+    if (PAIR) {          // work = (pair m-tile, n-tile); this CTA owns rows [rank*128, rank*128 + 128) of the pair tile
+      n_tile = work % p.n_tiles;
+      m_tile = 2 * (work / p.n_tiles) + rank;
     } else {
       const int tile = work / p.splits;
       split = work - tile * p.splits;
@@ -469,7 +453,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     epilogue_loop<MODE, GEGLU, TC, false>(&tmC, &tmR, p, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), rfull0,
-                                          (int)blockIdx.x, (int)gridDim.x, total_tiles * p.splits, 0, 0);
+                                          (int)blockIdx.x, (int)gridDim.x, total_tiles * p.splits, 0);
   }
 
   tc_fence_before();
@@ -505,24 +489,6 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-// multicast forms: the box lands at the same shared-memory offset of every CTA in `mask`, and each of them signals
-// (the leader of its pair's) mbarrier at the offset of `bar`
-__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
-                                                    uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_pair_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1,
-                                                    int c2, int c3, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
-      : "memory");
-}
 __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                uint32_t accumulate) {
   const uint32_t z0 = 0, z1 = 0, z2 = 0, z3 = 0, z4 = 0, z5 = 0, z6 = 0, z7 = 0;   // disable-output-lane masks
@@ -550,7 +516,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols
 }
 
 template <int MODE, bool GEGLU, typename TC>
-__global__ void __launch_bounds__(num_threads(GEGLU), 1)      // cluster of 2 * p.mc CTAs (launch attribute)
+__global__ void __launch_bounds__(num_threads(GEGLU), 1)      // cluster of 2 CTAs (launch attribute)
 tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -567,27 +533,19 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * EPI_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();
-  const uint32_t rank = crank & 1u;                   // CTA inside its pair: which 128 of the 256 rows
-  const int q_pair = (int)(crank >> 1);               // pair inside the cluster: which n-tile of the group
+  const uint32_t rank = cluster_ctarank();            // CTA inside its pair: which 128 of the 256 rows
   const bool leader = rank == 0;
-  const int csize = 2 * p.mc;
-  const int pair_id = blockIdx.x / csize, num_pairs = gridDim.x / csize;     // cluster index / count
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   const int pair_m_tiles = (p.m_tiles + 1) >> 1;
-  const int n_groups = p.n_tiles / p.mc;
-  const int total_work = pair_m_tiles * n_groups;
+  const int total_work = pair_m_tiles * p.n_tiles;
   const int k_iters = p.taps * p.k_chunks;
-  const uint16_t all_mask = (uint16_t)((1u << csize) - 1u);
-  const uint16_t pair_mask = (uint16_t)(3u << (2 * q_pair));
-  const uint16_t a_mask = (uint16_t)((rank ? 0xAAAAu : 0x5555u) & all_mask);     // CTAs holding the same 128 rows
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmC);
     if (p.epi & PB_EPI_RESIDUAL) prefetch_tmap(&tmR);
-    // a stage is refilled by multicast from every pair of the cluster: all of them must have consumed it
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), (uint32_t)p.mc); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * num_teams(GEGLU)); }
     for (int s = 0; s < MAX_TEAMS * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
     fence_barrier_init();
@@ -607,42 +565,9 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================================================================== TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0, phase = 0;
-      const bool mc = p.mc > 1;
-      const uint32_t a_slice = (uint32_t)(q_pair * (A_STAGE_BYTES / p.mc));     // this CTA's share of the A tile
-      const int d1 = p.sl_d1[q_pair], d2 = p.sl_d2[q_pair], d3 = p.sl_d3[q_pair];
-      // look-ahead stream: the A box that will be loaded pf_dist k-iterations from now is prefetched into L2
-      int pf_work = pair_id, pf_it = 0, pf_x = 0, pf_y = 0, pf_n = 0, pf_m = 0;
-      auto pf_decode = [&]() {
-        pf_m = 2 * (pf_work / n_groups) + (int)rank;
-        if (MODE != PB_A_LINEAR) {
-          pf_x = (pf_m % p.tiles_x) * p.bw;
-          pf_y = ((pf_m / p.tiles_x) % p.tiles_y) * p.bh;
-          pf_n = (pf_m / (p.tiles_x * p.tiles_y)) * p.bn_img;
-        }
-      };
-      auto pf_advance = [&]() {
-        if (++pf_it == k_iters) { pf_it = 0; pf_work += num_pairs; if (pf_work < total_work) pf_decode(); }
-      };
-      auto pf_issue = [&]() {
-        if (pf_work >= total_work) return;
-        const int tap = pf_it / p.k_chunks, kc = pf_it - tap * p.k_chunks;
-        if (MODE == PB_A_LINEAR) {
-          tma_prefetch_2d(&tmA, kc * BLOCK_K, pf_m * BLOCK_M + d1);
-        } else if (MODE == PB_A_CONV3X3) {
-          const int ky = tap / 3, kx = tap - ky * 3;
-          if (mc) tma_prefetch_4d(&tmA, kc * BLOCK_K, pf_x + d1 + kx - 1, pf_y + d2 + ky - 1, pf_n + d3);
-          else tma_prefetch_4d(&tmA, kc * BLOCK_K, pf_x * p.cstride + kx - 1, pf_y * p.cstride + ky - 1, pf_n);
-        } else {
-          tma_prefetch_4d(&tmA, kc * BLOCK_K, pf_x + d1, pf_y + d2 + tap - 1, pf_n + d3);
-        }
-      };
-      if (p.pf_dist > 0) {
-        if (pf_work < total_work) pf_decode();
-        for (int i = 0; i < p.pf_dist; ++i) { pf_issue(); pf_advance(); }
-      }
       for (int work = pair_id; work < total_work; work += num_pairs) {
-        const int n_tile = (work % n_groups) * p.mc + q_pair;
-        const int m_tile = 2 * (work / n_groups) + (int)rank;
+        const int n_tile = work % p.n_tiles;
+        const int m_tile = 2 * (work / p.n_tiles) + (int)rank;
         int cx = 0, cy = 0, cn = 0;
         if (MODE != PB_A_LINEAR) {
           cx = (m_tile % p.tiles_x) * p.bw;
@@ -656,20 +581,14 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t b_dst = a_dst + A_STAGE_BYTES;
           if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)stage_bytes);   // bytes of BOTH CTAs
           if (MODE == PB_A_LINEAR) {
-            if (mc) tma_load_2d_pair_mc(a_dst + a_slice, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M + d1, a_mask);
-            else tma_load_2d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
+            tma_load_2d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
           } else if (MODE == PB_A_CONV3X3) {
             const int ky = tap / 3, kx = tap - ky * 3;
-            if (mc) tma_load_4d_pair_mc(a_dst + a_slice, &tmA, full_bar(stage), kc * BLOCK_K, cx + d1 + kx - 1,
-                                        cy + d2 + ky - 1, cn + d3, a_mask);       // stride 1 only
-            else tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx * p.cstride + kx - 1,
-                                  cy * p.cstride + ky - 1, cn);
+            tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx * p.cstride + kx - 1,
+                             cy * p.cstride + ky - 1, cn);
           } else {
-            if (mc) tma_load_4d_pair_mc(a_dst + a_slice, &tmA, full_bar(stage), kc * BLOCK_K, cx + d1, cy + d2 + tap - 1,
-                                        cn + d3, a_mask);
-            else tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
+            tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
           }
-          if (p.pf_dist > 0) { pf_issue(); pf_advance(); }
           const int kcol = it * BLOCK_K;
           // GEGLU: CTA 0 stages the value rows, CTA 1 the gate rows of the same output columns
           const int wrow = GEGLU ? (int)rank * p.geglu_half + n_tile * half_n : n_tile * p.block_n + (int)rank * half_n;
@@ -696,17 +615,17 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
-          umma_commit_pair(empty_bar(stage), all_mask);     // every CTA of the cluster may refill this stage
+          umma_commit_pair(empty_bar(stage), 3);      // both CTAs of the pair may refill this stage
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(tfull_bar(acc), pair_mask);
+        umma_commit_pair(tfull_bar(acc), 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     // ================================================================== epilogue (warps 2..9, both CTAs)
     epilogue_loop<MODE, GEGLU, TC, true>(&tmC, &tmR, p, tmem_base, epi_base, tfull_bar(0), tempty_bar(0), rfull0,
-                                         pair_id, num_pairs, total_work, (int)rank, q_pair);
+                                         pair_id, num_pairs, total_work, (int)rank);
   }
 
   tc_fence_before();
@@ -757,8 +676,42 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached per thread, keyed by everything that goes into the encoding (base pointer, shape,
+// strides, box, element strides, dtype, swizzle): the caching allocator hands the same addresses back forward after
+// forward, so an eager forward pays cuTensorMapEncodeTiled once per distinct operand instead of 4x per GEMM and 3-4x
+// per attention launch.  Direct-mapped, 1024 entries; a miss simply re-encodes.
+namespace {
+struct TmapKey {
+  const void* base;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5], estr[5];
+  int32_t dtype, swizzle, rank, pad;
+};
+struct TmapEntry {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int TMAP_CACHE = 1024;
+}  // namespace
+
 int encode_tmap(CUtensorMap* out, int dtype, int swizzle_bytes, const void* base, int rank, const uint64_t* dims,
                 const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  static thread_local TmapEntry* cache = nullptr;
+  if (cache == nullptr) cache = static_cast<TmapEntry*>(calloc(TMAP_CACHE, sizeof(TmapEntry)));
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base; key.dtype = dtype; key.swizzle = swizzle_bytes; key.rank = rank;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; key.estr[i] = elem_strides ? elem_strides[i] : 1; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  uint64_t h = 1469598103934665603ull;
+  const uint64_t* kw = reinterpret_cast<const uint64_t*>(&key);
+  for (size_t i = 0; i < sizeof(key) / 8; ++i) { h ^= kw[i]; h *= 1099511628211ull; }
+  TmapEntry* slot = cache ? &cache[(h ^ (h >> 29)) & (TMAP_CACHE - 1)] : nullptr;
+  if (slot && slot->valid && memcmp(&slot->key, &key, sizeof(key)) == 0) {
+    *out = slot->map;
+    return PB_OK;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -781,6 +734,7 @@ int encode_tmap(CUtensorMap* out, int dtype, int swizzle_bytes, const void* base
               (unsigned long long)(rank > 1 ? strides_bytes[0] : 0));
     return PB_ECUDA;
   }
+  if (slot) { slot->key = key; slot->map = *out; slot->valid = true; }
   return PB_OK;
 }
 
@@ -825,9 +779,6 @@ static int num_sms();
 // A width that is only a multiple of 16 is legal when it is the whole output (its ragged last chunk is clipped
 // at the tensor edge by the bulk store).
 static int pick_block_n(int n_cols, int cap, int m_tiles) {
-  // PB_TC_BN=<width>: tuning override (experiments only): use that tile width whenever it divides the output
-  static const int forced = []() { const char* e = getenv("PB_TC_BN"); return e ? atoi(e) : 0; }();
-  if (forced > 0 && forced <= cap && forced % 32 == 0 && n_cols % forced == 0) return forced;
   if (n_cols <= cap && n_cols % 16 == 0 && n_cols % 32 != 0) return n_cols;
   int best = 0;
   long best_cost = 0;
@@ -881,31 +832,29 @@ template <int MODE, bool GEGLU, typename TC>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                        const TcParams& p, size_t smem, cudaStream_t st) {
   static bool configured = false;
-  static int max_clusters[5] = {0, 0, 0, 0, 0};     // co-resident clusters per cluster shape (index = p.mc)
+  static int max_clusters = 0;                      // co-resident CTA pairs
   auto kern = tc_gemm_pair_kernel<MODE, GEGLU, TC>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_pair_kernel)");
     configured = true;
   }
-  const int csize = 2 * p.mc;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(num_threads(GEGLU)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
-  if (max_clusters[p.mc] == 0) {
-    cfg.gridDim = dim3((unsigned)(num_sms() / csize * csize));
+  if (max_clusters == 0) {
+    cfg.gridDim = dim3((unsigned)(num_sms() / 2 * 2));
     int n = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-    if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / csize; }
-    max_clusters[p.mc] = n;
-    if (getenv("PB_TC_DEBUG")) fprintf(stderr, "pandora_b200: cluster of %d CTAs: %d co-resident clusters\n", csize, n);
+    if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / 2; }
+    max_clusters = n;
   }
-  int clusters = ((p.m_tiles + 1) / 2) * (p.n_tiles / p.mc);
-  if (clusters > max_clusters[p.mc]) clusters = max_clusters[p.mc];
-  cfg.gridDim = dim3((unsigned)(clusters * csize));
+  int clusters = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  if (clusters > max_clusters) clusters = max_clusters;
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, p);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_gemm_pair_kernel)");
   PB_LAUNCH_CHECK("tc_gemm_pair_kernel");
@@ -1063,47 +1012,14 @@ static int tc_plan(const pb_gemm_args* a, TcPlan* pl) {
     p.bias = nullptr; p.rowbias = nullptr;
   }
   // CTA pairs whenever there are enough 256-row tiles to occupy the 74 SM pairs and no split-K
-  static const bool pair_enabled = []() { const char* e = getenv("PB_TC_PAIR"); return !(e && e[0] == '0'); }();
   p.pair = 0;
-  if (pair_enabled && p.splits == 1 && p.m_tiles >= 2) {
+  if (p.splits == 1 && p.m_tiles >= 2) {
     const int pm = (p.m_tiles + 1) / 2;
     const int bn_pair = pick_block_n(n_cols, geglu ? 128 : 256, 2 * pm);   // waves counted over 74 pairs ~ 148 / 2
     if (bn_pair >= 32 && (long)pm * (n_cols / bn_pair) * 2 >= num_sms() / 2) {
       p.pair = 1;
       p.block_n = geglu ? 2 * bn_pair : bn_pair;
       p.n_tiles = n_cols / bn_pair;
-    }
-  }
-  // A multicast across the pairs of a cluster (same rows, neighbouring n-tiles).  A slice = 128/mc consecutive rows of
-  // the tile = a sub-brick of the A box; conv stride 2 keeps the plain pair kernel.
-  p.mc = 1;
-  static const int mc_cap = []() { const char* e = getenv("PB_TC_MC"); return e ? atoi(e) : 1; }();
-  if (p.pair && mc_cap > 1 && !(a->a_mode == PB_A_CONV3X3 && a->stride != 1) && (long)p.m_tiles * BLOCK_M == a->M) {
-    for (int mc = 4; mc >= 2; mc >>= 1) {
-      if (mc > mc_cap || p.n_tiles % mc != 0) continue;
-      // enough clusters to fill the machine
-      if ((long)((p.m_tiles + 1) / 2) * (p.n_tiles / mc) * 2 * mc < num_sms() / 2) continue;
-      const int rs = BLOCK_M / mc;       // rows per slice
-      bool ok = true;
-      if (a->a_mode == PB_A_LINEAR) {
-        for (int q = 0; q < mc; ++q) { p.sl_d1[q] = q * rs; p.sl_d2[q] = 0; p.sl_d3[q] = 0; }
-        pl->abox[1] = (uint32_t)rs;
-      } else {
-        const int bw = p.bw, bh = p.bh;
-        int sw, sh, sn;
-        if (rs % (bw * bh) == 0) { sw = bw; sh = bh; sn = rs / (bw * bh); }
-        else if ((bw * bh) % rs == 0 && rs % bw == 0) { sw = bw; sh = rs / bw; sn = 1; }
-        else if (bw % rs == 0) { sw = rs; sh = 1; sn = 1; }
-        else { ok = false; sw = sh = sn = 1; }
-        if (ok) {
-          for (int q = 0; q < mc; ++q) {
-            const int r0 = q * rs;                         // first tile row of the slice
-            p.sl_d1[q] = r0 % bw; p.sl_d2[q] = (r0 / bw) % bh; p.sl_d3[q] = r0 / (bw * bh);
-          }
-          pl->abox[1] = (uint32_t)sw; pl->abox[2] = (uint32_t)sh; pl->abox[3] = (uint32_t)sn;
-        }
-      }
-      if (ok) { p.mc = mc; break; }
     }
   }
   // fused GroupNorm column statistics: fp32 output written by this kernel itself, slabs aligned in row space
@@ -1171,16 +1087,10 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   }
   // long-K tiles visit the epilogue rarely: one staging slot per team is enough and the ring gets the bytes
   p.epi_slots = (p.taps * p.k_chunks / p.splits >= 16) ? 1 : EPI_SLOTS;
-  static const int slots_force = []() { const char* e = getenv("PB_TC_SLOTS"); return e ? atoi(e) : 0; }();
-  if (slots_force == 1 || slots_force == 2) p.epi_slots = slots_force;
-  static const int pf_force = []() { const char* e = getenv("PB_TC_PF"); return e ? atoi(e) : -1; }();
-  p.pf_dist = pf_force >= 0 ? pf_force : 0;
   const int epi_bytes = num_teams(geglu) * p.epi_slots * p.slot_bytes;
   const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = (SMEM_TOTAL - 1024 - epi_bytes - BAR_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  static const int stage_cap = []() { const char* e = getenv("PB_TC_STAGES"); return e ? atoi(e) : 0; }();   // experiments
-  if (stage_cap >= 2 && p.stages > stage_cap) p.stages = stage_cap;
   if (p.stages < 2) TC_UNSUPPORTED("pb_tc_gemm: tile does not fit shared memory");
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment slack*/ + epi_bytes + BAR_BYTES;
 
