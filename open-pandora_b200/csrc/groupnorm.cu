@@ -319,6 +319,15 @@ struct GnFold {
   float eps;
 };
 
+// y * sigmoid(y) in 6 instructions: one FMUL into the exponent, MUFU ex2, FADD, MUFU rcp, FMUL (the flush-to-zero
+// approximations are ~2 ulp, far inside the rounding of the bf16 / fp32 operand that is written)
+__device__ __forceinline__ float silu_fast(float y) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return y * r;
+}
+
 // Apply pass.  A CTA owns `rows_per_cta` consecutive rows of one instance and walks them as ONE flat stream of 4-channel
 // vectors (thread t takes vectors t, t + 256, ...: every thread busy for any channel count, neighbouring threads on
 // neighbouring 16-byte words), 4 loads in flight per thread.  The per-channel affine (scale, shift) is built once per CTA
@@ -372,43 +381,59 @@ gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int
     }
   }
   __syncthreads();
+  // Flat walk over nrows x cv vectors.  Everything inside the CTA is 32-bit: vector offsets relative to the CTA's first
+  // row (the host bounds rows_per_cta so that they fit), advanced incrementally — one step is 256 vectors = (drow rows,
+  // dcol columns), with a wrap into the next row.
   const int total = nrows * cv;
-  const int drow = GN_THREADS / cv, dcol = GN_THREADS - drow * cv;      // one step of 256 vectors in (row, column)
-  int row = (int)threadIdx.x / cv, col = (int)threadIdx.x - row * cv;
-  for (int i = threadIdx.x; i < total; i += 4 * GN_THREADS) {
+  const int ldxv = (int)(ldx >> 2), ldyv = (int)(ldy >> 2);
+  const int drow = GN_THREADS / cv, dcol = GN_THREADS - drow * cv;
+  const int stepx = drow * ldxv + dcol, stepy = drow * ldyv + dcol, wrapx = ldxv - cv, wrapy = ldyv - cv;
+  int col = (int)threadIdx.x % cv;
+  int offx = ((int)threadIdx.x / cv) * ldxv + col, offy = ((int)threadIdx.x / cv) * ldyv + col;
+  auto advance = [&]() {
+    col += dcol; offx += stepx; offy += stepy;
+    if (col >= cv) { col -= cv; offx += wrapx; offy += wrapy; }
+  };
+  auto emit = [&](const float (&t)[4], int c, int oy) {
+    const float4 a = gn_ab[c], b = gn_ab[cv + c];
+    float o[4];
+    o[0] = fmaf(t[0], a.x, b.x); o[1] = fmaf(t[1], a.y, b.y);
+    o[2] = fmaf(t[2], a.z, b.z); o[3] = fmaf(t[3], a.w, b.w);
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = silu_fast(o[j]);
+    }
+    store4(yb + (int64_t)oy * 4, o);
+  };
+  int i = threadIdx.x;
+  for (; i + 3 * GN_THREADS < total; i += 4 * GN_THREADS) {      // 4 independent 16-byte loads in flight per thread
     float t[4][4];
-    int rr[4], cc[4];
+    int cc[4], oy[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      rr[u] = row; cc[u] = col;
-      if (i + u * GN_THREADS < total) load4(xb + (int64_t)row * ldx + col * 4, t[u]);
-      row += drow; col += dcol;
-      if (col >= cv) { col -= cv; ++row; }
+      cc[u] = col; oy[u] = offy;
+      load4(xb + (int64_t)offx * 4, t[u]);
+      advance();
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (i + u * GN_THREADS < total) {
-        const float4 a = gn_ab[cc[u]], b = gn_ab[cv + cc[u]];
-        float o[4];
-        o[0] = fmaf(t[u][0], a.x, b.x); o[1] = fmaf(t[u][1], a.y, b.y);
-        o[2] = fmaf(t[u][2], a.z, b.z); o[3] = fmaf(t[u][3], a.w, b.w);
-        if (silu) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = silu_f(o[j]);
-        }
-        store4(yb + (int64_t)rr[u] * ldy + cc[u] * 4, o);
-      }
-    }
+    for (int u = 0; u < 4; ++u) emit(t[u], cc[u], oy[u]);
+  }
+  for (; i < total; i += GN_THREADS) {
+    float t[4];
+    load4(xb + (int64_t)offx * 4, t);
+    emit(t, col, offy);
+    advance();
   }
 }
 
 // rows per CTA of the apply pass: ~6 CTAs per SM over the whole launch, at least 16 rows, at most what int32 indexing holds
-static inline int gn_apply_rows(int64_t n_inst, int64_t R, int64_t C) {
+static inline int gn_apply_rows(int64_t n_inst, int64_t R, int64_t C, int64_t ld_max) {
   int64_t rows = ceil_div(n_inst * R, (int64_t)148 * 6);
   if (rows < 16) rows = 16;
   if (rows > R) rows = R;
-  const int64_t cap = ((int64_t)1 << 30) / (C / 4);
+  const int64_t cap = ((int64_t)1 << 30) / (ld_max / 4 + 1);      // 32-bit vector offsets inside a CTA
   if (rows > cap) rows = cap;
+  (void)C;
   return (int)rows;
 }
 
@@ -502,7 +527,7 @@ int pb_groupnorm_apply_cols(const void* x, int32_t x_dtype, int64_t ldx, void* y
   gn_cols_partial_kernel<<<pgrid, 256, 0, st>>>(colstats, ld_colstats, (int)C, groups, rows_per_inst, splits,
                                                 reinterpret_cast<double*>(ws));
   PB_LAUNCH_CHECK("gn_cols_partial_kernel");
-  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C);
+  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C, ldx > ldy ? ldx : ldy);
   dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
   const size_t smem = (size_t)C * 2 * sizeof(float);
   GnFold fold;
@@ -568,7 +593,7 @@ int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int
   PB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "pb_groupnorm_apply: need C %% 4 == 0, ld %% 4 == 0");
   PB_REQUIRE(C <= GN_MAX_C, "pb_groupnorm_apply: C <= %d supported", GN_MAX_C);
   cudaStream_t st = to_stream(stream);
-  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C);
+  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C, ldx > ldy ? ldx : ldy);
   dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
   const size_t smem = (size_t)C * 2 * sizeof(float);
   PB_DISPATCH_DTYPE(x_dtype, TXT, {
