@@ -78,6 +78,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// The same packing on the integer pipe (round half up: +0x8000, keep the high halves) for finite non-negative
+// inputs — the softmax probabilities.  F2FP shares the quarter-rate XU pipe with MUFU ex2 (measured: XU 65 % busy with
+// 96 ex2 + 64 F2FP per thread and key tile), and that pipe is what bounds d = 64 attention.
+__device__ __forceinline__ uint32_t pack_bf16_alu(float a, float b) {
+  return __byte_perm(__float_as_uint(a) + 0x8000u, __float_as_uint(b) + 0x8000u, 0x7632);
+}
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -272,7 +278,7 @@ tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const int col = c * 32 + i;
-            w[i >> 1] = pack_bf16(v[c][i] * (col < sp ? i1 : i2), v[c][i + 1] * (col + 1 < sp ? i1 : i2));
+            w[i >> 1] = pack_bf16_alu(v[c][i] * (col < sp ? i1 : i2), v[c][i + 1] * (col + 1 < sp ? i1 : i2));
           }
           tmem_st16(lane_addr + (uint32_t)(c * 16), w);       // P aliases the head of S: 32 keys = 16 packed columns
         }
@@ -512,7 +518,6 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         if (did) { idle = 0; continue; }
-        __nanosleep(32);                 // nothing ready: do not compete with the softmax warps for issue slots
         if (++idle > (1u << 24)) {
           printf("pandora_b200: attention issuer timeout (block %d,%d,%d s %d/%d pv %d/%d)\n", blockIdx.x, blockIdx.y,
                  blockIdx.z, s_iss[0], s_iss[1], pv_iss[0], pv_iss[1]);
@@ -580,7 +585,7 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             if (EMU > 0 && ((i >> 1) % (EMU > 0 ? EMU : 1)) == (EMU > 0 ? EMU : 1) - 1) exp2_fma2(p0, p1, e0, e1);
             else { p0 = fast_exp2(e0); p1 = fast_exp2(e1); }
             add2(lq[(i & 2)], lq[(i & 2) + 1], p0, p1);
-            w[c][i >> 1] = pack_bf16(p0, p1);
+            w[c][i >> 1] = pack_bf16_alu(p0, p1);
           }
         } else {
 #pragma unroll
@@ -588,7 +593,7 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const float p0 = (c * 32 + i < valid) ? fast_exp2(fmaf(v[c][i], p.scale_log2, neg_m)) : 0.f;
             const float p1 = (c * 32 + i + 1 < valid) ? fast_exp2(fmaf(v[c][i + 1], p.scale_log2, neg_m)) : 0.f;
             lq[(i >> 1) & 3] += p0 + p1;
-            w[c][i >> 1] = pack_bf16(p0, p1);
+            w[c][i >> 1] = pack_bf16_alu(p0, p1);
           }
         }
       }

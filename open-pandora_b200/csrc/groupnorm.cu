@@ -319,14 +319,39 @@ struct GnFold {
   float eps;
 };
 
-// y * sigmoid(y) in 6 instructions: one FMUL into the exponent, MUFU ex2, FADD, MUFU rcp, FMUL (the flush-to-zero
-// approximations are ~2 ulp, far inside the rounding of the bf16 / fp32 operand that is written)
+// y * sigmoid(y).  The quarter-rate XU pipe (MUFU + conversions) is what a streaming norm+SiLU pass runs out of first
+// (2 MUFU + the bf16 conversion per element is 60 % of that pipe at the HBM rate), so:
+//   bf16 output: sigmoid(y) = 0.5 + 0.5 tanh(y / 2) with ONE MUFU (tanh.approx, max relative error 2^-11, an eighth of
+//                the bf16 rounding that follows): h = y/2, h + h * tanh(h); the conversion is done on the integer pipe;
+//   fp32 output: ex2 + rcp (~2 ulp), the exact mode's budget.
+template <bool LOWP>
 __device__ __forceinline__ float silu_fast(float y) {
+  if (LOWP) {
+    const float h = 0.5f * y;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+  }
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y * -1.4426950408889634f));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return y * r;
 }
+// four floats -> four bf16 (round to nearest even) on the integer pipe; finite inputs
+__device__ __forceinline__ void store4_bf16_alu(bf16* p, const float (&v)[4]) {
+  uint32_t u[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t x = __float_as_uint(v[j]);
+    u[j] = x + 0x7FFFu + ((x >> 16) & 1u);
+  }
+  uint2 t;
+  t.x = __byte_perm(u[0], u[1], 0x7632);
+  t.y = __byte_perm(u[2], u[3], 0x7632);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+__device__ __forceinline__ void store4_fast(bf16* p, const float (&v)[4]) { store4_bf16_alu(p, v); }
+__device__ __forceinline__ void store4_fast(float* p, const float (&v)[4]) { store4(p, v); }
 
 // Apply pass.  A CTA owns `rows_per_cta` consecutive rows of one instance and walks them as ONE flat stream of 4-channel
 // vectors (thread t takes vectors t, t + 256, ...: every thread busy for any channel count, neighbouring threads on
@@ -401,9 +426,9 @@ gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int
     o[2] = fmaf(t[2], a.z, b.z); o[3] = fmaf(t[3], a.w, b.w);
     if (silu) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) o[j] = silu_fast(o[j]);
+      for (int j = 0; j < 4; ++j) o[j] = silu_fast<sizeof(TY_) == 2>(o[j]);
     }
-    store4(yb + (int64_t)oy * 4, o);
+    store4_fast(yb + (int64_t)oy * 4, o);
   };
   int i = threadIdx.x;
   for (; i + 3 * GN_THREADS < total; i += 4 * GN_THREADS) {      // 4 independent 16-byte loads in flight per thread
