@@ -138,10 +138,20 @@ size_t pb_groupnorm_apply_cols_ws_bytes(int64_t n_inst, int64_t rows_per_inst, i
 int pb_groupnorm_apply_cols(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,
                             const float* colstats, int64_t ld_colstats, int64_t n_inst, int64_t rows_per_inst,
                             int64_t C, int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
-                            void* ws, size_t ws_bytes, pb_stream_t stream);
+                            void* ws, size_t ws_bytes, void* x_copy, int64_t ld_copy, pb_stream_t stream);
+/* x_copy (optional, NULL = off): the apply pass also writes x itself, converted to y's dtype, with row pitch ld_copy —
+ * the bf16 operand of a ResBlock's 1x1 skip convolution (openaimodel3d.py:190,233), which reads the same trunk tensor
+ * the norm reads, without a second pass over it.                                                        */
 int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype,
                        int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
-                       const float* scale_shift, int32_t silu, pb_stream_t stream);
+                       const float* scale_shift, int32_t silu, void* x_copy, int64_t ld_copy, pb_stream_t stream);
+
+/* GroupNorm(+SiLU) of SMALL instances in ONE launch (a CTA per (instance, group) sums its slab and streams it again out
+ * of L1 / L2 to apply): for the deep levels whose tensors take ~2 us to move, where three launches dominate.
+ * PB_EUNSUPPORTED when C/groups is not a multiple of 4 or a slab exceeds 4 Mi elements.                  */
+int pb_groupnorm_small(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,
+                       int64_t n_inst, int64_t rows_per_inst, int64_t C, int32_t groups, float eps, const float* gamma,
+                       const float* beta, int32_t silu, pb_stream_t stream);
 
 /* Sequence-parallel split of pb_groupnorm_stats (temporal blocks normalise over ALL frames and pixels of a
  * clip, openaimodel3d.py:259, attention.py:331,368, while a rank holds a slice): pb_groupnorm_sums writes this

@@ -142,8 +142,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src,
 }
 
 // NCH = 32-key chunks of the score row held in registers: 3 (n_kv <= 96: the 77 + 16 cross-attention keys; 2 CTAs per
-// SM) or 4 (n_kv <= 128; one CTA per SM, the 128-value row does not fit 168 registers)
-template <int NCH>
+// SM) or 4 (n_kv <= 128; one CTA per SM, the 128-value row does not fit 168 registers).
+// CSP / CNK > 0: the segment split and key count are compile-time constants (the Open-Pandora context is always 77 text
+// + 16 image tokens per frame): every per-key segment test folds away; 0 = runtime values.
+template <int NCH, int CSP, int CNK>
 __global__ void __launch_bounds__(192, NCH == 3 ? 2 : 1)
 tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttP p) {
@@ -231,7 +233,7 @@ tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const uint32_t o_addr = lane_addr + X_O_COL0;
-    const int sp = p.split > 0 ? p.split : p.nkv, nk = p.nkv;
+    const int sp = CNK > 0 ? CSP : (p.split > 0 ? p.split : p.nkv), nk = CNK > 0 ? CNK : p.nkv;
     const int nchunk = (nk + 31) >> 5;          // <= NCH
     const bool tma_out = p.o_tma != 0;
     const bool leader = warp == 2 && lane == 0;
@@ -243,20 +245,22 @@ tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int c = 0; c < NCH; ++c)
         if (c < nchunk) tmem_ld32(lane_addr + c * 32, v[c]);
       tmem_ld_wait();
-      float mx1 = -INFINITY, mx2 = -INFINITY;
+      // four independent chains per segment (a single fmaxf / add chain over 93 values is 93 dependent instructions)
+      float m1[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, m2[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         if (c < nchunk) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int col = c * 32 + i;
-            mx1 = fmaxf(mx1, col < sp ? v[c][i] : -INFINITY);
-            mx2 = fmaxf(mx2, (col >= sp && col < nk) ? v[c][i] : -INFINITY);
+            if (col < sp) m1[i & 3] = fmaxf(m1[i & 3], v[c][i]);
+            else if (col < nk) m2[i & 3] = fmaxf(m2[i & 3], v[c][i]);
           }
         }
       }
-      mx1 *= p.scale_log2; mx2 *= p.scale_log2;
-      float l1 = 0.f, l2 = 0.f;
+      const float mx1 = fmaxf(fmaxf(m1[0], m1[1]), fmaxf(m1[2], m1[3])) * p.scale_log2;
+      const float mx2 = fmaxf(fmaxf(m2[0], m2[1]), fmaxf(m2[2], m2[3])) * p.scale_log2;
+      float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         if (c < nchunk) {
@@ -264,12 +268,13 @@ tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           for (int i = 0; i < 32; ++i) {
             const int col = c * 32 + i;
             float e = 0.f;
-            if (col < sp) { e = fast_exp2(fmaf(v[c][i], p.scale_log2, -mx1)); l1 += e; }
-            else if (col < nk) { e = fast_exp2(fmaf(v[c][i], p.scale_log2, -mx2)); l2 += e; }
+            if (col < sp) { e = fast_exp2(fmaf(v[c][i], p.scale_log2, -mx1)); s1[i & 3] += e; }
+            else if (col < nk) { e = fast_exp2(fmaf(v[c][i], p.scale_log2, -mx2)); s2[i & 3] += e; }
             v[c][i] = e;
           }
         }
       }
+      const float l1 = (s1[0] + s1[1]) + (s1[2] + s1[3]), l2 = (s2[0] + s2[1]) + (s2[2] + s2[3]);
       const float i1 = 1.0f / l1, i2 = l2 > 0.f ? 1.0f / l2 : 0.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -714,9 +719,11 @@ extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
   const size_t smem_x = X_SMEM + 1024 + 8 * X_NBARS + 16;
   const size_t smem_v3 = V3_SMEM + 1024 + 8 * V3_NBARS + 16;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_attention_x_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
+    cudaError_t e = cudaFuncSetAttribute(tc_attention_x_kernel<3, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc_attention_x_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
+      e = cudaFuncSetAttribute(tc_attention_x_kernel<3, 77, 93>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc_attention_x_kernel<4, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_attention3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_attention3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_attention3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3);
@@ -746,8 +753,10 @@ extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
       if ((rc = encode_rows3d(&to, oo, cols, a->n_q, a->batch)) != PB_OK) return rc;
     }
     dim3 grid((unsigned)ceil_div(q_tiles, best), (unsigned)a->heads, (unsigned)a->batch);
-    if (narrow) tc_attention_x_kernel<3><<<grid, 192, smem_x, to_stream(stream)>>>(tq, tk, tv, to, p);
-    else tc_attention_x_kernel<4><<<grid, 192, smem_x, to_stream(stream)>>>(tq, tk, tv, to, p);
+    if (a->kv_split == 77 && a->n_kv == 93)
+      tc_attention_x_kernel<3, 77, 93><<<grid, 192, smem_x, to_stream(stream)>>>(tq, tk, tv, to, p);
+    else if (narrow) tc_attention_x_kernel<3, 0, 0><<<grid, 192, smem_x, to_stream(stream)>>>(tq, tk, tv, to, p);
+    else tc_attention_x_kernel<4, 0, 0><<<grid, 192, smem_x, to_stream(stream)>>>(tq, tk, tv, to, p);
   } else {
     dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM * 2), (unsigned)a->heads, (unsigned)a->batch);
     // share of the exponentials computed on the FMA pipe instead of the MUFU (tuning knob while the split is being

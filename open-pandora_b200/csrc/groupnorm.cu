@@ -363,7 +363,8 @@ __device__ __forceinline__ void store4_fast(float* p, const float (&v)[4]) { sto
 template <typename TX_, typename TY_>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int64_t R, int C,
-                const float* __restrict__ scale_shift, int silu, int rows_per_cta, GnFold fold) {
+                const float* __restrict__ scale_shift, int silu, int rows_per_cta, GnFold fold,
+                TY_* __restrict__ xc /* optional: plain copy of x in y's dtype, row pitch ldc */, int64_t ldc) {
   extern __shared__ float4 gn_ab[];               // [cv] scale vectors, then [cv] shift vectors
   __shared__ float g_mean[32], g_rstd[32];
   const int inst = blockIdx.y;
@@ -372,6 +373,7 @@ gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int
   const int nrows = (int)(r_begin + rows_per_cta < R ? rows_per_cta : R - r_begin);
   const TX_* xb = x + ((int64_t)inst * R + r_begin) * ldx;
   TY_* yb = y + ((int64_t)inst * R + r_begin) * ldy;
+  TY_* cb = xc == nullptr ? nullptr : xc + ((int64_t)inst * R + r_begin) * ldc;
   if (fold.part != nullptr) {
     if (threadIdx.x < fold.G) {
       const double* pp = fold.part + ((int64_t)inst * fold.G + threadIdx.x) * fold.splits * 2;
@@ -412,14 +414,18 @@ gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int
   const int total = nrows * cv;
   const int ldxv = (int)(ldx >> 2), ldyv = (int)(ldy >> 2);
   const int drow = GN_THREADS / cv, dcol = GN_THREADS - drow * cv;
+  const int ldcv = (int)(ldc >> 2);
   const int stepx = drow * ldxv + dcol, stepy = drow * ldyv + dcol, wrapx = ldxv - cv, wrapy = ldyv - cv;
+  const int stepc = drow * ldcv + dcol, wrapc = ldcv - cv;
   int col = (int)threadIdx.x % cv;
   int offx = ((int)threadIdx.x / cv) * ldxv + col, offy = ((int)threadIdx.x / cv) * ldyv + col;
+  int offc = ((int)threadIdx.x / cv) * ldcv + col;
   auto advance = [&]() {
-    col += dcol; offx += stepx; offy += stepy;
-    if (col >= cv) { col -= cv; offx += wrapx; offy += wrapy; }
+    col += dcol; offx += stepx; offy += stepy; offc += stepc;
+    if (col >= cv) { col -= cv; offx += wrapx; offy += wrapy; offc += wrapc; }
   };
-  auto emit = [&](const float (&t)[4], int c, int oy) {
+  auto emit = [&](const float (&t)[4], int c, int oy, int oc) {
+    if (cb != nullptr) store4_fast(cb + (int64_t)oc * 4, t);
     const float4 a = gn_ab[c], b = gn_ab[cv + c];
     float o[4];
     o[0] = fmaf(t[0], a.x, b.x); o[1] = fmaf(t[1], a.y, b.y);
@@ -433,21 +439,88 @@ gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int
   int i = threadIdx.x;
   for (; i + 3 * GN_THREADS < total; i += 4 * GN_THREADS) {      // 4 independent 16-byte loads in flight per thread
     float t[4][4];
-    int cc[4], oy[4];
+    int cc[4], oy[4], oc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      cc[u] = col; oy[u] = offy;
+      cc[u] = col; oy[u] = offy; oc[u] = offc;
       load4(xb + (int64_t)offx * 4, t[u]);
       advance();
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) emit(t[u], cc[u], oy[u]);
+    for (int u = 0; u < 4; ++u) emit(t[u], cc[u], oy[u], oc[u]);
   }
   for (; i < total; i += GN_THREADS) {
     float t[4];
     load4(xb + (int64_t)offx * 4, t);
-    emit(t, col, offy);
+    emit(t, col, offy, offc);
     advance();
+  }
+}
+
+// One launch for SMALL instances (the H/8 and H/4 levels, where the producer left no column statistics): a CTA owns one
+// (instance, group) — R rows x C/G channels, a few KB to ~100 KB — sums it, and streams it a second time (now an L1 / L2
+// hit) to apply the affine (+SiLU).  Replaces partial + finalize + apply (three launches of ~7 us each on tensors that
+// take ~2 us to move).  Needs C/G % 4 == 0.
+template <typename TX_, typename TY_>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_group_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int R, int C, int G, float eps,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int silu) {
+  __shared__ double red[2][GN_THREADS / 32];
+  __shared__ float stat[2];
+  const int inst = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / G, vpg = cpg >> 2;
+  const TX_* xb = x + (int64_t)inst * R * ldx + g * cpg;
+  TY_* yb = y + (int64_t)inst * R * ldy + g * cpg;
+  const int total = R * vpg;
+  const int drow = GN_THREADS / vpg, dcol = GN_THREADS - drow * vpg;
+  int row = (int)threadIdx.x / vpg, col = (int)threadIdx.x - row * vpg;
+  float s = 0.f, q = 0.f;
+  {
+    int r = row, c = col;
+    for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+      float t[4];
+      load4(xb + (int64_t)r * ldx + c * 4, t);
+      s += (t[0] + t[1]) + (t[2] + t[3]);
+      q += (t[0] * t[0] + t[1] * t[1]) + (t[2] * t[2] + t[3] * t[3]);
+      r += drow; c += dcol;
+      if (c >= vpg) { c -= vpg; ++r; }
+    }
+  }
+  double sd = (double)s, qd = (double)q;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    qd += __shfl_xor_sync(0xffffffffu, qd, o);
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][w] = sd; red[1][w] = qd; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ss = 0.0, qq = 0.0;
+    for (int i = 0; i < GN_THREADS / 32; ++i) { ss += red[0][i]; qq += red[1][i]; }
+    const double cnt = (double)R * cpg;
+    const double mean = ss / cnt;
+    double var = qq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[0] = (float)mean;
+    stat[1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float mean = stat[0], rstd = stat[1];
+  for (int i = threadIdx.x; i < total; i += GN_THREADS) {
+    float t[4], gm[4], bt[4], o[4];
+    load4(xb + (int64_t)row * ldx + col * 4, t);
+    load4(gamma + g * cpg + col * 4, gm);
+    load4(beta + g * cpg + col * 4, bt);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = rstd * gm[j];
+      o[j] = fmaf(t[j], a, bt[j] - mean * a);
+      if (silu) o[j] = silu_fast<sizeof(TY_) == 2>(o[j]);
+    }
+    store4_fast(yb + (int64_t)row * ldy + col * 4, o);
+    row += drow; col += dcol;
+    if (col >= vpg) { col -= vpg; ++row; }
   }
 }
 
@@ -536,7 +609,7 @@ int pb_groupnorm_stats_cols(const float* colstats, int64_t ld_colstats, int64_t 
 int pb_groupnorm_apply_cols(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,
                             const float* colstats, int64_t ld_colstats, int64_t n_inst, int64_t rows_per_inst,
                             int64_t C, int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
-                            void* ws, size_t ws_bytes, pb_stream_t stream) {
+                            void* ws, size_t ws_bytes, void* x_copy, int64_t ld_copy, pb_stream_t stream) {
   using namespace pb;
   PB_REQUIRE(x && y && colstats && gamma && beta && ws, "pb_groupnorm_apply_cols: null pointer");
   PB_REQUIRE(n_inst > 0 && n_inst <= 65535 && rows_per_inst > 0 && C > 0 && groups > 0 && groups <= 32 &&
@@ -552,7 +625,7 @@ int pb_groupnorm_apply_cols(const void* x, int32_t x_dtype, int64_t ldx, void* y
   gn_cols_partial_kernel<<<pgrid, 256, 0, st>>>(colstats, ld_colstats, (int)C, groups, rows_per_inst, splits,
                                                 reinterpret_cast<double*>(ws));
   PB_LAUNCH_CHECK("gn_cols_partial_kernel");
-  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C, ldx > ldy ? ldx : ldy);
+  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C, (ldx > ldy ? ldx : ldy) > ld_copy ? (ldx > ldy ? ldx : ldy) : ld_copy);
   dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
   const size_t smem = (size_t)C * 2 * sizeof(float);
   GnFold fold;
@@ -562,7 +635,8 @@ int pb_groupnorm_apply_cols(const void* x, int32_t x_dtype, int64_t ldx, void* y
     PB_DISPATCH_DTYPE(y_dtype, TYT, {
       gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, smem, st>>>(reinterpret_cast<const TXT*>(x), ldx,
                                                                 reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
-                                                                nullptr, silu, rows_per_cta, fold);
+                                                                nullptr, silu, rows_per_cta, fold,
+                                                                reinterpret_cast<TYT*>(x_copy), ld_copy);
     })
   })
   PB_LAUNCH_CHECK("gn_apply_kernel");
@@ -611,14 +685,14 @@ int pb_groupnorm_affine(const double* sums, int64_t n_inst, int64_t C, int32_t g
 
 int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype,
                        int64_t ldy, int64_t n_inst, int64_t rows_per_inst, int64_t C,
-                       const float* scale_shift, int32_t silu, pb_stream_t stream) {
+                       const float* scale_shift, int32_t silu, void* x_copy, int64_t ld_copy, pb_stream_t stream) {
   using namespace pb;
   PB_REQUIRE(x && y && scale_shift, "pb_groupnorm_apply: null pointer");
   PB_REQUIRE(n_inst > 0 && n_inst <= 65535 && rows_per_inst > 0 && C > 0, "pb_groupnorm_apply: bad sizes");
   PB_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "pb_groupnorm_apply: need C %% 4 == 0, ld %% 4 == 0");
   PB_REQUIRE(C <= GN_MAX_C, "pb_groupnorm_apply: C <= %d supported", GN_MAX_C);
   cudaStream_t st = to_stream(stream);
-  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C, ldx > ldy ? ldx : ldy);
+  const int rows_per_cta = gn_apply_rows(n_inst, rows_per_inst, C, (ldx > ldy ? ldx : ldy) > ld_copy ? (ldx > ldy ? ldx : ldy) : ld_copy);
   dim3 grid((unsigned)ceil_div(rows_per_inst, rows_per_cta), (unsigned)n_inst);
   const size_t smem = (size_t)C * 2 * sizeof(float);
   PB_DISPATCH_DTYPE(x_dtype, TXT, {
@@ -627,10 +701,34 @@ int pb_groupnorm_apply(const void* x, int32_t x_dtype, int64_t ldx, void* y, int
       memset(&nofold, 0, sizeof(nofold));
       gn_apply_kernel<TXT, TYT><<<grid, GN_THREADS, smem, st>>>(reinterpret_cast<const TXT*>(x), ldx,
                                                                 reinterpret_cast<TYT*>(y), ldy, rows_per_inst, (int)C,
-                                                                scale_shift, silu, rows_per_cta, nofold);
+                                                                scale_shift, silu, rows_per_cta, nofold,
+                                                                reinterpret_cast<TYT*>(x_copy), ld_copy);
     })
   })
   PB_LAUNCH_CHECK("gn_apply_kernel");
+  return PB_OK;
+}
+
+int pb_groupnorm_small(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,
+                       int64_t n_inst, int64_t rows_per_inst, int64_t C, int32_t groups, float eps, const float* gamma,
+                       const float* beta, int32_t silu, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(x && y && gamma && beta, "pb_groupnorm_small: null pointer");
+  PB_REQUIRE(n_inst > 0 && n_inst <= 65535 && rows_per_inst > 0 && C > 0 && groups > 0 && C % groups == 0,
+             "pb_groupnorm_small: bad sizes");
+  if ((C / groups) % 4 != 0 || ldx % 4 != 0 || ldy % 4 != 0 || rows_per_inst * (C / groups) > (1 << 22)) {
+    set_error("pb_groupnorm_small: needs C/groups %% 4 == 0 and at most 4 Mi elements per (instance, group)");
+    return PB_EUNSUPPORTED;
+  }
+  dim3 grid((unsigned)groups, (unsigned)n_inst);
+  PB_DISPATCH_DTYPE(x_dtype, TXT, {
+    PB_DISPATCH_DTYPE(y_dtype, TYT, {
+      gn_group_kernel<TXT, TYT><<<grid, GN_THREADS, 0, to_stream(stream)>>>(
+          reinterpret_cast<const TXT*>(x), ldx, reinterpret_cast<TYT*>(y), ldy, (int)rows_per_inst, (int)C, groups, eps,
+          gamma, beta, silu);
+    })
+  })
+  PB_LAUNCH_CHECK("gn_group_kernel");
   return PB_OK;
 }
 

@@ -81,11 +81,12 @@ SYMBOLS = {
     "pb_groupnorm_cols_ws_bytes": (_sz, [_i64, _i64, _i32]),
     "pb_groupnorm_apply_cols_ws_bytes": (_sz, [_i64, _i64, _i32]),
     "pb_groupnorm_apply_cols": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp,
-                                          _i32, _vp, _sz, _vp]),
+                                          _i32, _vp, _sz, _vp, _i64, _vp]),
     "pb_groupnorm_stats_cols": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pb_groupnorm_ws_bytes": (_sz, [_i64, _i64, _i64]),
     "pb_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "pb_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _i32, _vp]),
+    "pb_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _vp, _i32, _vp, _i64, _vp]),
+    "pb_groupnorm_small": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _i64, _i32, _f, _vp, _vp, _i32, _vp]),
     "pb_groupnorm_sums": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "pb_groupnorm_affine": (C.c_int, [_vp, _i64, _i64, _i32, C.c_double, _f, _vp, _vp, _vp, _vp]),
     "pb_layernorm": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _f, _vp]),
@@ -270,15 +271,18 @@ def gemm(a, w, c, bias=None, rowbias=None, rowbias_rows=0, residual=None, geglu=
     return 2 if wrote_stats else 1
 
 
-def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32, colstats=None):
+def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32, colstats=None, x_copy=None):
     """y = GroupNorm(x) [* SiLU]; x, y 2-D row views [n_inst*rows_per_inst, C].  colstats: the column statistics
-    the producer of x left behind (see `gemm`), which replace the statistics pass over x."""
+    the producer of x left behind (see `gemm`), which replace the statistics pass over x.  x_copy: optional row view of
+    y's dtype that receives x itself (converted) from the same pass."""
     global launches
     lib = load()
     Cc = x.shape[1]
     xp, ldx = _rows(x)
     yp, ldy = _rows(y)
     st = _stream()
+    cp_, ldcp = (None, 0) if x_copy is None else _rows(x_copy)
+    assert x_copy is None or (x_copy.dtype == y.dtype and x_copy.shape == x.shape)
     if colstats is not None:
         assert rows_per_inst % 32 == 0 and colstats.shape[0] * 32 == x.shape[0] and colstats.shape[1] == 2 * Cc
         cp, ldcs = _rows(colstats)
@@ -286,12 +290,24 @@ def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32, co
         wsb = lib.pb_groupnorm_apply_cols_ws_bytes(n_inst, rows_per_inst, groups)
         ws = torch.empty(wsb // 8, dtype=torch.float64, device=x.device)
         _check(lib.pb_groupnorm_apply_cols(xp, dt(x), ldx, yp, dt(y), ldy, cp, ldcs, n_inst, rows_per_inst, Cc, groups,
-                                           eps, gamma.data_ptr(), beta.data_ptr(), int(silu), ws.data_ptr(), wsb, st),
-               "pb_groupnorm_apply_cols")
+                                           eps, gamma.data_ptr(), beta.data_ptr(), int(silu), ws.data_ptr(), wsb, cp_, ldcp,
+                                           st), "pb_groupnorm_apply_cols")
         _tock(tok)
         launches += 2
         return None
     else:
+        # small tensors (<= 8 MiB): one launch, a CTA per (instance, group); the second pass over the slab hits L1 / L2
+        if x_copy is None and x.numel() * x.element_size() <= (8 << 20) and n_inst * groups >= 32 \
+                and (Cc // groups) % 4 == 0:
+            tok = _tick("groupnorm_small", 0, _nbytes(x) + _nbytes(y), f"inst{n_inst} rows{rows_per_inst} C{Cc}")
+            rc = lib.pb_groupnorm_small(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc, groups, eps,
+                                        gamma.data_ptr(), beta.data_ptr(), int(silu), st)
+            if rc == 0:
+                _tock(tok)
+                launches += 1
+                return None
+            if rc != E_UNSUPPORTED:
+                _check(rc, "pb_groupnorm_small")
         ws_bytes = lib.pb_groupnorm_ws_bytes(n_inst, rows_per_inst, Cc)
         ws = torch.empty(ws_bytes // 4 + n_inst * 2 * Cc, dtype=torch.float32, device=x.device)
         stats = ws[ws_bytes // 4:]
@@ -301,7 +317,7 @@ def groupnorm(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, groups=32, co
                "pb_groupnorm_stats")
         launches += 3
     _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc,
-                                  stats.data_ptr(), int(silu), st), "pb_groupnorm_apply")
+                                  stats.data_ptr(), int(silu), cp_, ldcp, st), "pb_groupnorm_apply")
     _tock(tok)
     return stats
 
@@ -324,7 +340,7 @@ def groupnorm_sp(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, all_reduce
     _check(lib.pb_groupnorm_affine(sums.data_ptr(), n_inst, Cc, groups, float(global_rows * (Cc // groups)), eps,
                                    gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), st), "pb_groupnorm_affine")
     _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc,
-                                  stats.data_ptr(), int(silu), st), "pb_groupnorm_apply")
+                                  stats.data_ptr(), int(silu), None, 0, st), "pb_groupnorm_apply")
     launches += 4
 
 
@@ -383,7 +399,7 @@ def groupnorm_sp_peers(x, y, n_inst, rows_per_inst, gamma, beta, eps, silu, my_s
                                       float(global_rows * (Cc // groups)), eps, gamma.data_ptr(), beta.data_ptr(),
                                       stats.data_ptr(), st), "pb_sp_groupnorm_affine")
     _check(lib.pb_groupnorm_apply(xp, dt(x), ldx, yp, dt(y), ldy, n_inst, rows_per_inst, Cc,
-                                  stats.data_ptr(), int(silu), st), "pb_groupnorm_apply")
+                                  stats.data_ptr(), int(silu), None, 0, st), "pb_groupnorm_apply")
     launches += 4
 
 

@@ -458,9 +458,10 @@ class _Runner:
         abi.copy_rows(a, y)
         return y
 
-    def gn(self, x, prefix, n_inst, eps, silu, out_dtype=None, clip_wide=False):
+    def gn(self, x, prefix, n_inst, eps, silu, out_dtype=None, clip_wide=False, x_copy=None):
         """clip_wide: statistics span all frames and pixels of a sample (temporal blocks); under sequence
-        parallelism every rank holds a slice, so the (sum, sumsq) pairs are all-reduced."""
+        parallelism every rank holds a slice, so the (sum, sumsq) pairs are all-reduced.
+        x_copy: row tensor (operand dtype) that receives x itself from the same pass (operand of a 1x1 skip conv)."""
         y = self.new(x.shape[0], x.shape[1], out_dtype or self.opdt)
         rows = x.shape[0] // n_inst
         if clip_wide and self.sp is not None:
@@ -471,7 +472,7 @@ class _Runner:
             if cs is None or not states or rows % 32 or not all(q["valid"] for q in states):
                 cs = None
             abi.groupnorm(x, y, n_inst, rows, self.vec(prefix + "weight"), self.vec(prefix + "bias"), eps, silu,
-                          colstats=cs)
+                          colstats=cs, x_copy=x_copy)
         return y
 
     def ln(self, x, prefix):
@@ -508,7 +509,10 @@ class _Runner:
         can write there directly; the caller copies otherwise."""
         p = blk._pfx
         rows_per_sample = self.T * H * W
-        a = self.gn(x, p + "in_layers.0.", self.b * self.T, 1e-5, True)
+        # the 1x1 skip conv (channel change) reads x as a GEMM operand: the norm pass leaves the converted copy behind
+        has_skip = not isinstance(blk.skip_connection, nn.Identity)
+        x_op = self.new(x.shape[0], x.shape[1], self.opdt) if (has_skip and x.dtype != self.opdt) else None
+        a = self.gn(x, p + "in_layers.0.", self.b * self.T, 1e-5, True, x_copy=x_op)
         off, n = self.emb_slices[p]
         # tensors that only feed a GroupNorm (see UNetModel.bf16_norm_inputs)
         mid_dt = self.opdt if (self.use_tc and self.m.bf16_norm_inputs) else torch.float32
@@ -518,7 +522,8 @@ class _Runner:
         if isinstance(blk.skip_connection, nn.Identity):
             skip = x
         else:
-            skip = self.linear(x, p + "skip_connection.weight", p + "skip_connection.bias", torch.float32)
+            skip = self.linear(x if x_op is None else x_op, p + "skip_connection.weight", p + "skip_connection.bias",
+                               torch.float32)
         tconv_sp = blk.use_temporal_conv and self.sp is not None
         h = self.conv3x3(a, p + "out_layers.3.weight", p + "out_layers.3.bias", H, W, torch.float32, residual=skip,
                          stats=True, out=(self._send_slot(x.shape[0], blk.out_channels) if tconv_sp else

@@ -116,6 +116,37 @@ def test_groupnorm(abi, xdt, n_inst, R, C, silu, eps):
         assert rel_l2(y, ref) < tol(ydt)
 
 
+@pytest.mark.parametrize("n_inst,R,C", [(2, 640, 1280), (32, 40, 1280), (16, 160, 640), (1, 333, 128)])
+def test_groupnorm_single_launch_small_instances(abi, n_inst, R, C):
+    """Small tensors take the one-launch kernel (a CTA per (instance, group)); same result as the three-pass path."""
+    x = rnd(n_inst * R, C, seed=23) * 3 - 0.4
+    gamma, beta = 1 + 0.1 * rnd(C, seed=24), 0.1 * rnd(C, seed=25)
+    ref = F.group_norm(x.double().reshape(n_inst, R, C).permute(0, 2, 1), 32, gamma.double(), beta.double(), 1e-5)
+    ref = F.silu(ref).permute(0, 2, 1).reshape(n_inst * R, C)
+    l0 = abi.launches
+    y = torch.empty(n_inst * R, C, device="cuda")
+    abi.groupnorm(x, y, n_inst, R, gamma, beta, 1e-5, True)
+    assert abi.launches - l0 == (1 if n_inst * 32 >= 32 else 3)
+    assert rel_l2(y, ref) < 2e-6
+    yb = torch.empty(n_inst * R, C, device="cuda", dtype=torch.bfloat16)
+    abi.groupnorm(x, yb, n_inst, R, gamma, beta, 1e-5, True)
+    assert rel_l2(yb, ref) < 4e-3
+
+
+def test_groupnorm_leaves_operand_copy_of_its_input(abi):
+    """x_copy: the apply pass also writes x itself in the output dtype (the 1x1 skip conv's operand)."""
+    n_inst, R, C = 4, 2560, 320
+    x = rnd(n_inst * R, C, seed=26) * 2
+    gamma, beta = 1 + 0.1 * rnd(C, seed=27), 0.1 * rnd(C, seed=28)
+    y = torch.empty(n_inst * R, C, device="cuda", dtype=torch.bfloat16)
+    wide = torch.zeros(n_inst * R, C + 64, device="cuda", dtype=torch.bfloat16)
+    abi.groupnorm(x, y, n_inst, R, gamma, beta, 1e-5, True, x_copy=wide[:, 64:])
+    assert torch.equal(wide[:, 64:], x.to(torch.bfloat16)) and bool((wide[:, :64] == 0).all())
+    y2 = torch.empty_like(y)
+    abi.groupnorm(x, y2, n_inst, R, gamma, beta, 1e-5, True)
+    assert torch.equal(y, y2)
+
+
 @pytest.mark.parametrize("xdt", DT)
 @pytest.mark.parametrize("rows,C", [(77, 64), (1000, 320), (33, 512), (64, 640), (9, 1280)])
 def test_layernorm(abi, xdt, rows, C):
