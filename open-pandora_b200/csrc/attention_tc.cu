@@ -372,41 +372,6 @@ tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // TMEM columns: S_0 [0,128) S_1 [128,256) P_0 [256,320) P_1 [320,384) O_0 [384,448) O_1 [448,512).
 // (Measured on the version this replaces, where S_t,j+1 could only be issued after PV_t,j because P aliased S:
 // 39 % of the softmax warps' samples were spent waiting for the next score tile, tensor pipe 26 % active.)
-// 2^x on the FMA pipe for two values at once (packed fp32x2): Cody-Waite split x = n + f with n = round(x) taken from
-// the mantissa of x + 1.5 * 2^23, 2^f (f in [-0.5, 0.5]) by a cubic (max relative error 2.1e-4, a twentieth of the
-// bf16 rounding that follows), 2^n added into the exponent field.  The softmax of d = 64 attention is bound by the
-// MUFU ex2 rate (256 FLOP of tensor work per exponential): a fraction of the exponentials is computed here instead
-// (the FlashAttention-4 device).  Valid for x <= 127; clamped below at 2^-126.
-__device__ __forceinline__ void exp2_fma2(float& p0, float& p1, float x0, float x1) {
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
-  float t0, t1;
-  asm("{\n"
-      ".reg .b64 x, t, n, f, p, k;\n"
-      "mov.b64 x, {%4, %5};\n"
-      "mov.b64 k, {%6, %6};\n"
-      "add.rn.f32x2 t, x, k;\n"
-      "mov.b64 k, {%7, %7};\n"
-      "add.rn.f32x2 n, t, k;\n"
-      "mov.b64 k, {%8, %8};\n"
-      "fma.rn.f32x2 f, n, k, x;\n"
-      "mov.b64 p, {%9, %9};\n"
-      "mov.b64 k, {%10, %10};\n"
-      "fma.rn.f32x2 p, f, p, k;\n"
-      "mov.b64 k, {%11, %11};\n"
-      "fma.rn.f32x2 p, p, f, k;\n"
-      "mov.b64 k, {%12, %12};\n"
-      "fma.rn.f32x2 p, p, f, k;\n"
-      "mov.b64 {%0, %1}, p;\n"
-      "mov.b64 {%2, %3}, t;\n"
-      "}"
-      : "=f"(p0), "=f"(p1), "=f"(t0), "=f"(t1)
-      : "f"(x0), "f"(x1), "f"(12582912.0f), "f"(-12582912.0f), "f"(-1.0f), "f"(0.055838343f), "f"(0.24203594f),
-        "f"(0.69313675f), "f"(1.0f));
-  p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-}
-
 constexpr int V3_STAGES = 4;
 constexpr int V3_SMEM = TILE_BYTES * (2 + 2 * V3_STAGES);      // Q x2 + (K, V) x4 = 160 KiB
 constexpr float V3_RESCALE_THRESHOLD = 8.0f;                    // log2 units
@@ -416,8 +381,6 @@ constexpr int V3_NBARS = 1 + 2 * V3_STAGES + 8;                 // q_full, kv_fu
 // 384 threads = three warpgroups: {TMA producer, MMA issuer, two idle warps} | softmax of query tile 0 | softmax of
 // query tile 1.  setmaxnreg moves registers from the first warpgroup (88 each) to the softmax groups (208 each), so a
 // thread holds its whole 128-wide score row.
-// EMU: every EMU-th PAIR of exponentials goes to the FMA pipe (0 = all on the MUFU)
-template <int EMU>
 __global__ void __launch_bounds__(384, 1)
 tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttP p) {
@@ -585,10 +548,9 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (full) {                                       // no per-element key masking on all but the last tile
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            float e0, e1, p0, p1;
+            float e0, e1;
             fma2(e0, e1, v[c][i], v[c][i + 1], p.scale_log2, neg_m);
-            if (EMU > 0 && ((i >> 1) % (EMU > 0 ? EMU : 1)) == (EMU > 0 ? EMU : 1) - 1) exp2_fma2(p0, p1, e0, e1);
-            else { p0 = fast_exp2(e0); p1 = fast_exp2(e1); }
+            const float p0 = fast_exp2(e0), p1 = fast_exp2(e1);
             add2(lq[(i & 2)], lq[(i & 2) + 1], p0, p1);
             w[c][i >> 1] = pack_bf16_alu(p0, p1);
           }
@@ -724,10 +686,7 @@ extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
       e = cudaFuncSetAttribute(tc_attention_x_kernel<3, 77, 93>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(tc_attention_x_kernel<4, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_attention3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_attention3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_attention3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_attention3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_attention kernels)");
     configured = true;
   }
@@ -759,13 +718,7 @@ extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
     else tc_attention_x_kernel<4, 0, 0><<<grid, 192, smem_x, to_stream(stream)>>>(tq, tk, tv, to, p);
   } else {
     dim3 grid((unsigned)ceil_div(a->n_q, ATT_BM * 2), (unsigned)a->heads, (unsigned)a->batch);
-    // share of the exponentials computed on the FMA pipe instead of the MUFU (tuning knob while the split is being
-    // measured: PB_ATT_EMU = 0 | 2 | 3 | 4 -> none, every 2nd / 3rd / 4th pair)
-    static const int emu = []() { const char* e = getenv("PB_ATT_EMU"); return e ? atoi(e) : 4; }();
-    if (emu == 2) tc_attention3_kernel<2><<<grid, 384, smem_v3, to_stream(stream)>>>(tq, tk, tv, p);
-    else if (emu == 3) tc_attention3_kernel<3><<<grid, 384, smem_v3, to_stream(stream)>>>(tq, tk, tv, p);
-    else if (emu == 4) tc_attention3_kernel<4><<<grid, 384, smem_v3, to_stream(stream)>>>(tq, tk, tv, p);
-    else tc_attention3_kernel<0><<<grid, 384, smem_v3, to_stream(stream)>>>(tq, tk, tv, p);
+    tc_attention3_kernel<<<grid, 384, smem_v3, to_stream(stream)>>>(tq, tk, tv, p);
   }
   PB_LAUNCH_CHECK("tc_attention_kernel");
   return PB_OK;
