@@ -47,10 +47,11 @@ __host__ __device__ constexpr int num_threads(bool geglu) { return 64 + 128 * nu
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 8;
 constexpr int EPI_CHUNK = 32;                           // accumulator columns per epilogue chunk
-constexpr int EPI_SLOTS = 2;                            // staging slots per team
+constexpr int EPI_SLOTS = 2;                            // staging slots per team (default)
+constexpr int MAX_SLOTS = 3;                            // short-K tiles with a residual: 3 slots, residual loads 2 chunks ahead
 constexpr int EPI_SLOT_F32 = BLOCK_M * EPI_CHUNK * 4;   // 16 KiB: [128][32] fp32, 128B-swizzled rows
 constexpr int EPI_SLOT_BF16 = BLOCK_M * EPI_CHUNK * 2;  //  8 KiB: [128][32] bf16,  64B-swizzled rows
-constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 4 + MAX_TEAMS * EPI_SLOTS) + 16;
+constexpr int BAR_BYTES = 8 * (2 * MAX_STAGES + 4 + MAX_TEAMS * MAX_SLOTS) + 16;
 constexpr int SMEM_TOTAL = 227 * 1024;
 
 struct TcParams {
@@ -153,9 +154,11 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
   const int n_chunks = (out_cols + EPI_CHUNK - 1) / EPI_CHUNK;
   const int n_slots = p.epi_slots;
   const uint32_t slot_base = epi_base + (uint32_t)(team * n_slots * p.slot_bytes);
-  auto rfull = [&](int slot) { return rfull0 + 8u * (uint32_t)(team * EPI_SLOTS + slot); };
-  auto wait_slot_drained = [&]() { if (n_slots == 1) bulk_wait_read<0>(); else bulk_wait_read<EPI_SLOTS - 1>(); };
-
+  auto rfull = [&](int slot) { return rfull0 + 8u * (uint32_t)(team * MAX_SLOTS + slot); };
+  // no residual: slot cnt % S is rewritten once the store of chunk cnt - S has read it (S - 1 newer stores may be pending)
+  auto wait_slot_drained = [&]() {
+    if (n_slots == 1) bulk_wait_read<0>(); else if (n_slots == 2) bulk_wait_read<1>(); else bulk_wait_read<2>();
+  };
   // (work, chunk) -> tensor coordinates of the 128 x 32 output box
   auto coords = [&](int work, int ci, int (&c)[4], int& m_tile, int& n_tile) {
     int split = 0;
@@ -178,13 +181,28 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
     }
   };
 
+  // residual: the leader runs a prefetch stream `pf_dist` chunks ahead of the chunk being processed (2 with three slots:
+  // ncu showed the epilogue warps of the HBM-bound K = 320 layers waiting on a one-chunk-ahead load 17 % of the time).
+  // The slot of chunk cnt + D last held chunk cnt + D - S, so S - D newer stores (= 1 for S = 2, 3) may still be pending.
+  const int pf_dist = n_slots >= 3 ? 2 : 1;
+  int pf_work = first, pf_ci = team;
+  uint32_t pf_cnt = 0;
+  auto pf_issue = [&]() {
+    if (pf_work >= total || team >= n_chunks) return;
+    int nc[4], nmt, nnt;
+    coords(pf_work, pf_ci, nc, nmt, nnt);
+    const int sl = (int)(pf_cnt % (uint32_t)n_slots);
+    mbar_expect_tx(rfull(sl), (uint32_t)EPI_SLOT_F32);
+    tma_load_4d(slot_base + (uint32_t)(sl * p.slot_bytes), tmR, rfull(sl), nc[0], nc[1], nc[2], nc[3]);
+    ++pf_cnt;
+    pf_ci += NT;
+    if (pf_ci >= n_chunks) { pf_ci = team; pf_work += step; }
+  };
+
   int acc = 0, acc_phase = 0;
   uint32_t cnt = 0;          // chunks this team has processed: slot = cnt % SLOTS, parity = (cnt / SLOTS) & 1
-  if (RES && leader && first < total && team < n_chunks) {
-    int c[4], mt, nt;
-    coords(first, team, c, mt, nt);
-    mbar_expect_tx(rfull(0), (uint32_t)EPI_SLOT_F32);
-    tma_load_4d(slot_base, tmR, rfull(0), c[0], c[1], c[2], c[3]);
+  if (RES && leader) {
+    for (int i = 0; i < pf_dist; ++i) pf_issue();
   }
   for (int work = first; work < total; work += step) {
     int c[4], m_tile, n_tile;
@@ -311,17 +329,9 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
         coords(work, ci, c, m_tile, n_tile);
         tma_store_4d(tmC, sbuf, c[0], c[1], c[2], c[3]);
         bulk_commit();
-        if (RES) {
-          int nwork = work, nci = ci + NT;
-          if (nci >= n_chunks) { nci = team; nwork += step; }
-          if (nwork < total) {
-            const int nslot = (int)((cnt + 1) % (uint32_t)n_slots);
-            wait_slot_drained();                   // the store that last used that slot has drained it
-            int nc[4], nmt, nnt;
-            coords(nwork, nci, nc, nmt, nnt);
-            mbar_expect_tx(rfull(nslot), (uint32_t)EPI_SLOT_F32);
-            tma_load_4d(slot_base + (uint32_t)(nslot * p.slot_bytes), tmR, rfull(nslot), nc[0], nc[1], nc[2], nc[3]);
-          }
+        if (RES && pf_work < total) {
+          if (n_slots == 1) bulk_wait_read<0>(); else bulk_wait_read<1>();   // the store that last used that slot has drained it
+          pf_issue();
         }
       }
       ++cnt;
@@ -356,7 +366,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t rfull0 = bar_base + 8u * (2 * MAX_STAGES + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * EPI_SLOTS);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * MAX_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -369,7 +379,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.epi & PB_EPI_RESIDUAL) prefetch_tmap(&tmR);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4 * num_teams(GEGLU)); }
-    for (int s = 0; s < MAX_TEAMS * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
+    for (int s = 0; s < MAX_TEAMS * MAX_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -530,7 +540,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };   // one per CTA (multicast commit)
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };  // leader only, 16 arrivals
   const uint32_t rfull0 = bar_base + 8u * (2 * MAX_STAGES + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * EPI_SLOTS);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * MAX_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();            // CTA inside its pair: which 128 of the 256 rows
@@ -547,7 +557,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (p.epi & PB_EPI_RESIDUAL) prefetch_tmap(&tmR);
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * num_teams(GEGLU)); }
-    for (int s = 0; s < MAX_TEAMS * EPI_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
+    for (int s = 0; s < MAX_TEAMS * MAX_SLOTS; ++s) mbar_init(rfull0 + 8u * s, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -1087,6 +1097,10 @@ extern "C" int pb_tc_gemm(const pb_gemm_args* a, pb_stream_t stream) {
   }
   // long-K tiles visit the epilogue rarely: one staging slot per team is enough and the ring gets the bytes
   p.epi_slots = (p.taps * p.k_chunks / p.splits >= 16) ? 1 : EPI_SLOTS;
+  // short-K tiles with a residual are bound by the epilogue's HBM traffic: a third slot lets the residual loads run two
+  // chunks ahead (the ring only needs as many stages as the tile has k-steps)
+  // (measured: the Linear family of a 16x320x512 step 11.93 -> 11.41 ms)
+  if (res_in_kernel && !geglu && p.taps * p.k_chunks <= 12) p.epi_slots = MAX_SLOTS;
   const int epi_bytes = num_teams(geglu) * p.epi_slots * p.slot_bytes;
   const int stage_bytes = A_STAGE_BYTES + (p.pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = (SMEM_TOTAL - 1024 - epi_bytes - BAR_BYTES) / stage_bytes;
