@@ -281,6 +281,8 @@ def main():
         table, _ = sampler._step_table(False)
         g = GraphedCFGStep(sampler, unet, shape, cond, uc, fs, CFG_SCALE, RESCALE, 1.0, table)
         steps_ddpm = [int(s) for s in reversed(sampler.ddim_timesteps)]
+        sp_obj = unet.sequence_parallel
+        sp_bytes0 = sp_obj.bytes_moved if sp_obj is not None else 0
         if args.no_graph:
             def one_step(i):
                 g.ts.fill_(steps_ddpm[i % S_DDIM])
@@ -288,11 +290,15 @@ def main():
                 sampler._sync_noise(g.noise)
                 g._body()
             g._body(); g.step_index.zero_()
+            sp_passes = 1
         else:
             g.capture()
+            sp_passes = 2                              # eager warm-up + the captured pass
 
             def one_step(i):
                 g.step(steps_ddpm[i % S_DDIM])
+        # bytes this rank pulled from its peers per step (counted by the binding when the exchanges are enqueued)
+        nvlink_bytes = (sp_obj.bytes_moved - sp_bytes0) // sp_passes if sp_obj is not None else 0
 
         def timed(fn, n_warm_, n):
             g.reset(d["x"])
@@ -320,12 +326,7 @@ def main():
                    launches=launches, clocks=clk, graph=not args.no_graph,
                    parallelism=f"dp{n_clips}" + (f"xcfg{cfg_par}" if cfg_par > 1 else "") + (f"xsp{sp}" if sp > 1 else ""),
                    transport=getattr(unet.sequence_parallel, "transport", None), d=d, fs=fs)
-        sp_obj = unet.sequence_parallel
-        if sp_obj is not None:
-            b0 = sp_obj.bytes_moved
-            one_step(0)
-            torch.cuda.synchronize()
-            out["nvlink_bytes_per_step"] = sp_obj.bytes_moved - b0      # counted by the binding at enqueue time
+        out["nvlink_bytes_per_step"] = nvlink_bytes
         # ---- instrumented eager step: per-launch CUDA events -> breakdown + roofline of the GEMM family
         if instrument:
             g.step_index.zero_()

@@ -224,10 +224,6 @@ class SequenceParallel(_NcclTransport, _PullTransport):
         total = hdr + self.N_SLOTS * sums_bytes + self.N_SLOTS * slot_bytes
         group = self.group if self.group is not None else dist.group.WORLD
         name = group.group_name if hasattr(group, "group_name") else group
-        try:
-            symm_mem.enable_symm_mem_for_group(name)      # needed by older releases, a no-op / deprecated later
-        except Exception:
-            pass
         buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
         hdl = symm_mem.rendezvous(buf, name)
         buf.zero_()
