@@ -170,6 +170,13 @@ int pb_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y
                  int64_t rows, int64_t C, const float* gamma, const float* beta, float eps,
                  pb_stream_t stream);
 
+/* ---- row softmax -------------------------------------------------------------------------------
+ * y[r, :] = softmax(x[r, :] * scale): the score matrix of the VAE decoder's single-head, d = C AttnBlock
+ * (modules/networks/ae_modules.py:53-67: bmm, * C^-0.5, softmax over keys), between the two GEMMs that compute
+ * q k^T and P v.  x fp32 rows; y fp32 or bf16 rows.                                                */
+int pb_softmax_rows(const float* x, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy, int64_t rows, int64_t n,
+                    float scale, pb_stream_t stream);
+
 /* ---- attention ---------------------------------------------------------------------------------
  * out = softmax(q k^T * scale) v per (batch, head), head_dim 64.  Replaces the einsum/softmax/einsum
  * core of CrossAttention.forward (attention.py:101-125,129-135) and xformers

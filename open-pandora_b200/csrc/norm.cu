@@ -154,9 +154,75 @@ layernorm_rows_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y,
   }
 }
 
+// ---- row softmax (the single-head, d = C attention of the VAE decoder's AttnBlock, ae_modules.py:53-67: the score
+// matrix of one frame is [HW, HW] fp32 out of a GEMM; this turns every row into probabilities in the operand dtype of
+// the P V product).  One CTA per row, online (max, sum) in one pass, second pass writes.
+template <typename TY>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ x, int64_t ldx, TY* __restrict__ y, int64_t ldy, int n, float scale_log2) {
+  __shared__ float red_m[8], red_l[8];
+  const float* xr = x + (int64_t)blockIdx.x * ldx;
+  TY* yr = y + (int64_t)blockIdx.x * ldy;
+  const int nv = n >> 2;
+  float m = -INFINITY, l = 0.f;
+  for (int v = threadIdx.x; v < nv; v += 256) {
+    float t[4];
+    load4(xr + v * 4, t);
+    const float mv = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])) * scale_log2;
+    if (mv > m) { l *= exp2f(m - mv); m = mv; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) l += exp2f(fmaf(t[j], scale_log2, -m));
+  }
+  for (int i = nv * 4 + threadIdx.x; i < n; i += 256) {
+    const float s = xr[i] * scale_log2;
+    if (s > m) { l *= exp2f(m - s); m = s; }
+    l += exp2f(s - m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mm = fmaxf(m, m2);
+    l = (m == -INFINITY ? 0.f : l * exp2f(m - mm)) + (m2 == -INFINITY ? 0.f : l2 * exp2f(m2 - mm));
+    m = mm;
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red_m[w] = m; red_l[w] = l; }
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) M = fmaxf(M, red_m[i]);
+  float L = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) L += red_m[i] == -INFINITY ? 0.f : red_l[i] * exp2f(red_m[i] - M);
+  const float inv = 1.0f / L;
+  for (int v = threadIdx.x; v < nv; v += 256) {
+    float t[4], o[4];
+    load4(xr + v * 4, t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = exp2f(fmaf(t[j], scale_log2, -M)) * inv;
+    store4(yr + v * 4, o);
+  }
+  for (int i = nv * 4 + threadIdx.x; i < n; i += 256) yr[i] = from_f<TY>(exp2f(fmaf(xr[i], scale_log2, -M)) * inv);
+}
+
 }  // namespace pb
 
 extern "C" {
+
+int pb_softmax_rows(const float* x, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy, int64_t rows, int64_t n,
+                    float scale, pb_stream_t stream) {
+  using namespace pb;
+  PB_REQUIRE(x && y && rows > 0 && n > 0 && rows < ((int64_t)1 << 31) && n < ((int64_t)1 << 30), "pb_softmax_rows: bad arguments");
+  PB_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= n && ldy >= n, "pb_softmax_rows: row pitches must be multiples of 4");
+  const float scale_log2 = scale * 1.4426950408889634f;
+  PB_DISPATCH_DTYPE(y_dtype, TY, {
+    softmax_rows_kernel<TY><<<(unsigned)rows, 256, 0, to_stream(stream)>>>(x, ldx, reinterpret_cast<TY*>(y), ldy, (int)n,
+                                                                          scale_log2);
+  })
+  PB_LAUNCH_CHECK("softmax_rows_kernel");
+  return PB_OK;
+}
+
 
 int pb_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y_dtype, int64_t ldy,
                  int64_t rows, int64_t C, const float* gamma, const float* beta, float eps,

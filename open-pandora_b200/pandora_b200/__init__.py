@@ -14,9 +14,10 @@ from . import abi, config  # noqa: F401
 from .diffusion import DiffusionWrapper, LatentDiffusionLite  # noqa: F401
 from .sampler import DDIMSampler  # noqa: F401
 from .unet import UNetModel  # noqa: F401
+from .vae import AutoencoderKL, swap_vae_decoder  # noqa: F401
 
-__all__ = ["UNetModel", "DDIMSampler", "LatentDiffusionLite", "DiffusionWrapper", "install", "swap_unet", "abi",
-           "config"]
+__all__ = ["UNetModel", "DDIMSampler", "LatentDiffusionLite", "DiffusionWrapper", "AutoencoderKL", "install",
+           "swap_unet", "swap_vae_decoder", "abi", "config"]
 
 _UNET_MODULES = ("lvdm.modules.networks.openaimodel3d", "DynamiCrafter.lvdm.modules.networks.openaimodel3d")
 _DDIM_MODULES = ("lvdm.models.samplers.ddim", "DynamiCrafter.lvdm.models.samplers.ddim")

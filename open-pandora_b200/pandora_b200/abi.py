@@ -90,6 +90,7 @@ SYMBOLS = {
     "pb_groupnorm_sums": (C.c_int, [_vp, _i32, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _sz, _vp]),
     "pb_groupnorm_affine": (C.c_int, [_vp, _i64, _i64, _i32, C.c_double, _f, _vp, _vp, _vp, _vp]),
     "pb_layernorm": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _f, _vp]),
+    "pb_softmax_rows": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _i64, _i64, _f, _vp]),
     "pb_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pb_tc_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "pb_geglu": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _vp]),
@@ -410,6 +411,18 @@ def layernorm(x, y, gamma, beta, eps=1e-5):
     tok = _tick("layernorm", 0, _nbytes(x, y), f"rows{x.shape[0]} C{x.shape[1]}")
     _check(load().pb_layernorm(xp, dt(x), ldx, yp, dt(y), ldy, x.shape[0], x.shape[1],
                                gamma.data_ptr(), beta.data_ptr(), eps, _stream()), "pb_layernorm")
+    _tock(tok)
+    launches += 1
+
+
+def softmax_rows(x, y, scale):
+    """y[r] = softmax(x[r] * scale); x fp32 rows, y fp32 / bf16 rows of the same shape."""
+    global launches
+    assert x.dtype == torch.float32 and x.shape == y.shape
+    xp, ldx = _rows(x)
+    yp, ldy = _rows(y)
+    tok = _tick("softmax_rows", 0, _nbytes(x, y), f"rows{x.shape[0]} n{x.shape[1]}")
+    _check(load().pb_softmax_rows(xp, ldx, yp, dt(y), ldy, x.shape[0], x.shape[1], scale, _stream()), "pb_softmax_rows")
     _tock(tok)
     launches += 1
 

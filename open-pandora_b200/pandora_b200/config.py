@@ -48,6 +48,12 @@ DIFFUSION_512 = dict(
 )
 DIFFUSION_1024 = dict(DIFFUSION_512, base_scale=0.3)
 
+# First-stage (KL-VAE) configuration (`inference_512_v1.0.yaml:57-79`, identical for 1024) and the latent scale
+# factor of LatentDiffusion (`inference_512_v1.0.yaml:14`).
+VAE_DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                    ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+SCALE_FACTOR = 0.18215
+
 # Latent shapes (C, T, H, W) of the two headline resolutions.
 LATENT_512 = (4, 16, 40, 64)
 LATENT_1024 = (4, 16, 72, 128)

@@ -26,7 +26,7 @@ sys.path.insert(0, REF)
 
 from pandora_b200 import config as pcfg  # noqa: E402
 from pandora_b200.synthetic import randomize_module_, synth_inputs, synth_state_dict  # noqa: E402
-from oracle import ddim_oracle, unet_oracle  # noqa: E402
+from oracle import ddim_oracle, unet_oracle, vae_oracle  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -195,7 +195,47 @@ def full_width_case(name="full512", seed_w=1234, seed_x=0, stride=8):
                              dparams=pcfg.DIFFUSION_512, per_frame_image=True)))
 
 
+def vae_case(name, ddconfig, latent, seed_w, seed_x, scale_factor=0.18215):
+    """The reference's own AutoencoderKL.decode (lvdm/models/autoencoder.py:104-107) on synthetic weights: per-frame
+    decode of a small video latent, as LatentDiffusion.decode_core does (ddpm3d.py:630-651)."""
+    from lvdm.models.autoencoder import AutoencoderKL
+    m = AutoencoderKL(ddconfig=ddconfig, lossconfig={"target": "torch.nn.Identity"}, embed_dim=4).eval()
+    randomize_module_(m, seed_w)
+    sd = {k: v.detach() for k, v in m.state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))}
+    shapes = vae_oracle.vae_param_shapes(ddconfig)
+    assert set(shapes) == set(sd), set(shapes) ^ set(sd)
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    sd2 = synth_state_dict(shapes, seed_w)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+    z = synth_inputs(1, latent, 8, seed_x)["x"]                       # (1, 4, t, h, w) ~ N(0, 1)
+    zz = z.permute(0, 2, 1, 3, 4).reshape(-1, *z.shape[1:2], *z.shape[3:])
+    with torch.no_grad():
+        ref = torch.cat([m.decode((1.0 / scale_factor) * zz[i:i + 1]) for i in range(zz.shape[0])], 0)
+        ref64 = torch.cat([m.double().decode((1.0 / scale_factor) * zz[i:i + 1].double()) for i in range(zz.shape[0])], 0).float()
+    orc = vae_oracle.decode_first_stage(sd2, z, scale_factor)
+    ref5 = ref.reshape(1, zz.shape[0], *ref.shape[1:]).permute(0, 2, 1, 3, 4)
+    e = rel_l2(orc, ref5)
+    print(f"[vae:{name}] oracle vs reference fp32 rel-L2 = {e:.3e}; reference fp32 vs fp64 = {rel_l2(ref, ref64):.3e}; "
+          f"out std = {float(ref.std()):.3f}", flush=True)
+    assert e < 2e-5, e
+    np.savez_compressed(
+        os.path.join(GOLD, f"vae_{name}.npz"), y=ref5.numpy(),
+        y64=ref64.reshape(1, zz.shape[0], *ref.shape[1:]).permute(0, 2, 1, 3, 4).numpy(),
+        meta=json.dumps(dict(ddconfig=ddconfig, latent=list(latent), seed_w=seed_w, seed_x=seed_x,
+                             scale_factor=scale_factor, z_sum=float(z.double().sum()))))
+
+
+VAE_DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                    ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)   # inference_512_v1.0.yaml:62-76
+
+
 def main():
+    if "--vae" in sys.argv:          # first-stage decoder fixtures (SURVEY 8f row 1)
+        os.makedirs(GOLD, exist_ok=True)
+        torch.set_num_threads(os.cpu_count())
+        vae_case("full_width_8x12", VAE_DDCONFIG, (4, 2, 8, 12), 1234, 0)        # the real decoder, 2 frames, 64 x 96 px
+        vae_case("narrow_16x8", dict(VAE_DDCONFIG, ch=64), (4, 3, 16, 8), 77, 3)
+        return
     if "--full" in sys.argv:         # ~15 min of CPU: the full-width fixture only
         os.makedirs(GOLD, exist_ok=True)
         torch.set_num_threads(os.cpu_count())

@@ -162,3 +162,33 @@ print("DROP_IN_OK")
 ''' % (REF_DC, os.path.join(ROOT, "open-pandora_b200"), ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "DROP_IN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_vae_parameter_tree_matches_the_oracle_inventory_and_the_reference():
+    """The native AutoencoderKL reproduces the reference's state-dict keys and shapes: against the oracle's decoder
+    inventory always, and against the live reference class (strict load) when /root/reference is present."""
+    import os
+    import sys
+    import torch
+    from oracle import vae_oracle
+    from pandora_b200 import AutoencoderKL, config
+    m = AutoencoderKL(ddconfig=config.VAE_DDCONFIG, lossconfig={"target": "torch.nn.Identity"}, embed_dim=4)
+    own = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    want = vae_oracle.vae_param_shapes(config.VAE_DDCONFIG)
+    assert {k: v for k, v in own.items() if k.startswith(("decoder.", "post_quant_conv."))} == {k: tuple(v) for k, v in want.items()}
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m.decode(torch.zeros(1, 4, 8, 8))
+    ref_root = "/root/reference/DynamiCrafter"
+    if not os.path.isdir(ref_root):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, ref_root)
+    try:
+        from lvdm.models.autoencoder import AutoencoderKL as RefVAE
+    finally:
+        sys.path.remove(ref_root)
+    ref = RefVAE(ddconfig=config.VAE_DDCONFIG, lossconfig={"target": "torch.nn.Identity"}, embed_dim=4)
+    ref_sd = {k: v for k, v in ref.state_dict().items() if not k.startswith("loss.")}
+    assert {k: tuple(v.shape) for k, v in ref_sd.items()} == own
+    m.load_state_dict(ref_sd, strict=True)
+    shared = AutoencoderKL.from_reference(ref, config.VAE_DDCONFIG)
+    assert shared.decoder.conv_in.weight is ref.decoder.conv_in.weight

@@ -54,6 +54,18 @@ def test_unet_oracle_matches_full_width_reference_golden():
     assert rel_l2(y, z["y64"]) < 2e-5
 
 
+@pytest.mark.parametrize("name", ["vae_full_width_8x12", "vae_narrow_16x8"])
+def test_vae_decoder_oracle_matches_reference_golden(name):
+    """First-stage decoder: the oracle against `AutoencoderKL.decode` outputs of the reference itself."""
+    from oracle import vae_oracle
+    z, meta = load_golden(name)
+    sd = synth_state_dict(vae_oracle.vae_param_shapes(meta["ddconfig"]), meta["seed_w"])
+    lat = synth_inputs(1, tuple(meta["latent"]), 8, meta["seed_x"])["x"]
+    assert abs(float(lat.double().sum()) - meta["z_sum"]) < 1e-6 * max(1.0, abs(meta["z_sum"]))
+    y = vae_oracle.decode_first_stage(sd, lat, meta["scale_factor"])
+    assert rel_l2(y, z["y"]) < 2e-5 and rel_l2(y, z["y64"]) < 2e-5
+
+
 def test_param_inventory_full_size():
     from pandora_b200.config import UNET_512
     shapes = unet_oracle.unet_param_shapes(UNET_512)
