@@ -283,8 +283,15 @@ class _DecodeRunner(_Runner):
             a = self.gn(h, "decoder.norm_out.", n, 1e-6, True)
             y = self.gemm(a, w16, 16, f32, bias=b16, mode=abi.A_CONV3X3, conv=(h.shape[1], H, W, H, W, 1, 0), M=n * H * W)
         else:
+            # exact path: the CUDA-core GEMM moves 4-wide vectors -> pad the 3 output channels to 4
+            w4 = self.w(("convpad4", "decoder.conv_out.weight"), lambda: torch.cat(
+                [self.conv_w("decoder.conv_out.weight", f32), torch.zeros(4 - oc % 4 if oc % 4 else 0, 9 * h.shape[1],
+                                                                          dtype=f32, device=self.dev)], 0))
+            b4 = self.w(("vecpad4", "decoder.conv_out.bias"), lambda: torch.cat(
+                [self.vec("decoder.conv_out.bias"), torch.zeros(w4.shape[0] - oc, dtype=f32, device=self.dev)], 0))
             a = self.gn(h, "decoder.norm_out.", n, 1e-6, True, out_dtype=f32)
-            y = self.conv3x3(a, "decoder.conv_out.weight", "decoder.conv_out.bias", H, W, f32, wdtype=f32)
+            y = self.gemm(a, w4, w4.shape[0], f32, bias=b4, mode=abi.A_CONV3X3, conv=(h.shape[1], H, W, H, W, 1, 0),
+                          M=n * H * W, tc_ok=False)
         out = torch.empty((n, oc, 1, H, W), dtype=z.dtype, device=self.dev)
         abi.rows_to_video(y, out, n, oc, 1, H * W)          # reads the first oc columns of every row
         return out[:, :, 0]
