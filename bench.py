@@ -201,6 +201,52 @@ def torch_gpu_baseline(dev, d, fs):
     return out
 
 
+def vae_decode_leg(dev, latent):
+    """per-frame first-stage decode of one clip's latents (what follows the sampler every round,
+    ddpm3d.py:630-655) through the native AutoencoderKL.decode, bf16; device time of `decode_first_stage`."""
+    from pandora_b200 import AutoencoderKL, config
+    from pandora_b200.synthetic import randomize_module_, synth_inputs
+    dd = config.VAE_DDCONFIG
+    with torch.device(dev):
+        vae = AutoencoderKL(ddconfig=dd, embed_dim=4).eval()
+    randomize_module_(vae, 1234)
+    vae = vae.to(torch.bfloat16)
+    z = synth_inputs(1, latent, 8, 5)["x"].to(dev)
+    c, t, h, w = latent
+    # algorithmic FLOPs of Decoder.forward per frame: 2*M*N*K over the convolutions + 4*HW*HW*C for the attention
+    flops, ch, hw = 0.0, dd["ch"] * dd["ch_mult"][-1], h * w
+    conv = lambda cin, cout, px, k=9: 2.0 * px * cout * cin * k
+    flops += conv(dd["z_channels"], ch, hw) + 4 * conv(ch, ch, hw) + 4 * conv(ch, ch, hw, 1) + 4.0 * hw * hw * ch
+    cin = ch
+    for lv in reversed(range(len(dd["ch_mult"]))):
+        cout = dd["ch"] * dd["ch_mult"][lv]
+        for _ in range(dd["num_res_blocks"] + 1):
+            flops += conv(cin, cout, hw) + conv(cout, cout, hw) + (conv(cin, cout, hw, 1) if cin != cout else 0)
+            cin = cout
+        if lv:
+            hw *= 4
+            flops += conv(cin, cin, hw)
+    flops += conv(cin, dd["out_ch"], hw)
+    flops *= t
+    y = vae.decode_first_stage(z, config.SCALE_FACTOR)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = vae.decode_first_stage(z, config.SCALE_FACTOR)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = min(ts)
+    out = dict(workload=f"AutoencoderKL.decode of one clip's latents {list(latent)} -> {list(y.shape[1:])}, bf16, eager, "
+                        "frame by frame semantics (8 frames per pass)", ms_per_clip=round(ms, 2),
+               tflops=round(flops / ms / 1e9, 1), gflop_per_clip=round(flops / 1e9, 1))
+    del vae, y
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,6 +257,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true")
     ap.add_argument("--no-single-clip", action="store_true", help="skip the 16x576x1024 single-clip leg")
+    ap.add_argument("--no-vae", action="store_true", help="skip the first-stage decode leg")
     ap.add_argument("--sp", type=int, default=1, help="headline leg: sequence-parallel ways (ONE clip across this many ranks)")
     ap.add_argument("--cfg-par", type=int, default=1, choices=[1, 2],
                     help="headline leg: 2 = the cond / uncond branches of a step on two ranks")
@@ -444,6 +491,9 @@ def main():
                                    "a CFG step = 2 forwards")
     if rank == 0 and world == 1 and not args.no_torch_baseline and args.res == "512":
         torch_gpu = torch_gpu_baseline(dev, A["d"], A["fs"])
+    vae_leg = None
+    if rank == 0 and world == 1 and not args.no_vae:
+        vae_leg = vae_decode_leg(dev, tuple(A["latent"]))
     if rank == 0:
         sec_clip = A["sec_per_clip"]
         line = dict(metric=METRIC if args.res == "512" else METRIC.replace("320x512", "576x1024"), value=value,
@@ -467,6 +517,7 @@ def main():
                     gpu_launches=A["launches"], clocks=A["clocks"], roofline=roofline, cpu_baseline=cpu_baseline,
                     whole_step_tflops=round(whole, 1), whole_step_frac_of_peak=round(whole / pk["bf16"], 4),
                     sec_per_50_step_clip=round(sec_clip, 4), single_clip_1024=single, torch_gpu_baseline=torch_gpu,
+                    vae_decode=vae_leg,
                     breakdown=breakdown)
         print(json.dumps(line), flush=True)
     if world > 1:
