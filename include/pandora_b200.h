@@ -260,6 +260,15 @@ int pb_ddim_cfg_step(const float* x, const float* v_cond, const float* v_uncond,
                      float guidance_rescale, float temperature, const float* tables,
                      int32_t* step_index, int32_t advance, void* ws, size_t ws_bytes,
                      pb_stream_t stream);
+/* The same step for DDIMSampler_multicond.p_sample_ddim (models/samplers/ddim_multiplecond.py:211-283): a third
+ * U-Net output v_uncond_img (image conditioning kept, text dropped) and a second scale,
+ *   v = v_uncond + cfg_img*(v_uncond_img - v_uncond) + cfg_scale*(v_cond - v_uncond_img)        (:234)
+ * followed by the identical rescale / v->(eps,x0) / update.  v_uncond_img == NULL is pb_ddim_cfg_step.      */
+int pb_ddim_cfg3_step(const float* x, const float* v_cond, const float* v_uncond, const float* v_uncond_img,
+                      const float* noise, float* x_prev, float* pred_x0, int64_t batch, int64_t n,
+                      float cfg_scale, float cfg_img, float guidance_rescale, float temperature,
+                      const float* tables, int32_t* step_index, int32_t advance, void* ws, size_t ws_bytes,
+                      pb_stream_t stream);
 
 
 /* ---- sequence-parallel communication (one clip across P GPUs) ---------------------------------

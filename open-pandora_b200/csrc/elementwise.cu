@@ -115,16 +115,27 @@ __global__ void ddim_zero_ws_kernel(double* ws, int n) {
   if (i < n) ws[i] = 0.0;
 }
 
+// The guided prediction, rounded op by op like the reference's tensor expression:
+//   two branches   v_u + s*(v_c - v_u)                                            ddim.py:238
+//   three branches v_u + s_img*(v_ui - v_u) + s*(v_c - v_ui)                      ddim_multiplecond.py:234
+__device__ __forceinline__ float guided2(float c, float u, float s) {
+  return __fadd_rn(u, __fmul_rn(s, __fsub_rn(c, u)));
+}
+__device__ __forceinline__ float guided3(float c, float u, float ui, float s, float s_img) {
+  return __fadd_rn(__fadd_rn(u, __fmul_rn(s_img, __fsub_rn(ui, u))), __fmul_rn(s, __fsub_rn(c, ui)));
+}
+
 __global__ void __launch_bounds__(256)
-ddim_stats_kernel(const float* __restrict__ vc, const float* __restrict__ vu, int64_t n, float s,
-                  double* __restrict__ ws) {
+ddim_stats_kernel(const float* __restrict__ vc, const float* __restrict__ vu, const float* __restrict__ vi,
+                  int64_t n, float s, float s_img, double* __restrict__ ws) {
   const int b = blockIdx.y;
   const float* c = vc + (int64_t)b * n;
   const float* u = vu + (int64_t)b * n;
+  const float* ui = vi ? vi + (int64_t)b * n : nullptr;
   double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float x = c[i], y = u[i];
-    const float g = __fadd_rn(y, __fmul_rn(s, __fsub_rn(x, y)));
+    const float g = ui ? guided3(x, y, ui[i], s, s_img) : guided2(x, y, s);
     a0 += x; a1 += (double)x * x; a2 += g; a3 += (double)g * g;
   }
   __shared__ double red[4][8];
@@ -144,16 +155,16 @@ ddim_stats_kernel(const float* __restrict__ vc, const float* __restrict__ vu, in
 }
 
 // Arithmetic mirrors the reference op by op (separately rounded fp32 mul/add, no FMA contraction):
-//   v    = v_u + s*(v_c - v_u)                                  ddim.py:238
+//   v    = guided2 / guided3 above                              ddim.py:238, ddim_multiplecond.py:234
 //   v    = phi*(v*(std_c/std)) + (1-phi)*v                      utils_diffusion.py:152-157
 //   e    = sa*v + so*x ; x0 = sa*x - so*v                       ddpm3d.py:235-247
 //   x0  *= rescale                                              ddim.py:273-277
 //   xp   = sqrt(a_prev)*x0 + dir*e + sigma*noise*temperature    ddim.py:282-288
 __global__ void __launch_bounds__(256)
 ddim_update_kernel(const float* x /* may alias xp: in-place update of the graph's static latent */,
-                   const float* __restrict__ vc, const float* __restrict__ vu,
+                   const float* __restrict__ vc, const float* __restrict__ vu, const float* __restrict__ vi,
                    const float* __restrict__ noise, float* xp, float* __restrict__ x0o,
-                   int64_t n, float s, float phi, float temperature, const float* __restrict__ tables,
+                   int64_t n, float s, float s_img, float phi, float temperature, const float* __restrict__ tables,
                    const int32_t* __restrict__ step_index, const double* __restrict__ ws) {
   const int b = blockIdx.y;
   const float* tb = tables + (int64_t)(*step_index) * PB_DDIM_NCOEF;
@@ -173,7 +184,7 @@ ddim_update_kernel(const float* x /* may alias xp: in-place update of the graph'
     float v = c;
     if (vu != nullptr) {
       const float u = vu[off + i];
-      v = __fadd_rn(u, __fmul_rn(s, __fsub_rn(c, u)));
+      v = vi ? guided3(c, u, vi[off + i], s, s_img) : guided2(c, u, s);
       if (phi > 0.f)
         v = __fadd_rn(__fmul_rn(phi, __fmul_rn(v, ratio)), __fmul_rn(1.0f - phi, v));
     }
@@ -301,14 +312,15 @@ int pb_rows_to_video(const float* rows, int64_t ld, void* out, int32_t out_dtype
 
 size_t pb_ddim_ws_bytes(int64_t batch) { return batch > 0 ? (size_t)batch * 4 * sizeof(double) : 0; }
 
-int pb_ddim_cfg_step(const float* x, const float* v_cond, const float* v_uncond, const float* noise,
-                     float* x_prev, float* pred_x0, int64_t batch, int64_t n, float cfg_scale,
-                     float guidance_rescale, float temperature, const float* tables,
-                     int32_t* step_index, int32_t advance, void* ws, size_t ws_bytes,
-                     pb_stream_t stream) {
+int pb_ddim_cfg3_step(const float* x, const float* v_cond, const float* v_uncond, const float* v_uncond_img,
+                      const float* noise, float* x_prev, float* pred_x0, int64_t batch, int64_t n,
+                      float cfg_scale, float cfg_img, float guidance_rescale, float temperature,
+                      const float* tables, int32_t* step_index, int32_t advance, void* ws, size_t ws_bytes,
+                      pb_stream_t stream) {
   using namespace pb;
   PB_REQUIRE(x && v_cond && noise && x_prev && pred_x0 && tables && step_index, "pb_ddim_cfg_step: null pointer");
   PB_REQUIRE(batch > 0 && batch <= 65535 && n > 0, "pb_ddim_cfg_step: bad sizes");
+  PB_REQUIRE(v_uncond || !v_uncond_img, "pb_ddim_cfg3_step: the image-only branch needs the unconditional one");
   cudaStream_t st = to_stream(stream);
   const bool rescale = guidance_rescale > 0.f && v_uncond != nullptr;
   unsigned gx = grid_for(n, 256, 148 * 4);
@@ -317,18 +329,27 @@ int pb_ddim_cfg_step(const float* x, const float* v_cond, const float* v_uncond,
     double* w = reinterpret_cast<double*>(ws);
     ddim_zero_ws_kernel<<<(unsigned)ceil_div(batch * 4, 128), 128, 0, st>>>(w, (int)(batch * 4));
     PB_LAUNCH_CHECK("ddim_zero_ws_kernel");
-    ddim_stats_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(v_cond, v_uncond, n, cfg_scale, w);
+    ddim_stats_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(v_cond, v_uncond, v_uncond_img, n, cfg_scale, cfg_img, w);
     PB_LAUNCH_CHECK("ddim_stats_kernel");
   }
   ddim_update_kernel<<<dim3(gx, (unsigned)batch), 256, 0, st>>>(
-      x, v_cond, v_uncond, noise, x_prev, pred_x0, n, cfg_scale, rescale ? guidance_rescale : 0.f, temperature,
-      tables, step_index, reinterpret_cast<const double*>(ws));
+      x, v_cond, v_uncond, v_uncond_img, noise, x_prev, pred_x0, n, cfg_scale, cfg_img,
+      rescale ? guidance_rescale : 0.f, temperature, tables, step_index, reinterpret_cast<const double*>(ws));
   PB_LAUNCH_CHECK("ddim_update_kernel");
   if (advance) {
     ddim_advance_kernel<<<1, 1, 0, st>>>(step_index);
     PB_LAUNCH_CHECK("ddim_advance_kernel");
   }
   return PB_OK;
+}
+
+int pb_ddim_cfg_step(const float* x, const float* v_cond, const float* v_uncond, const float* noise,
+                     float* x_prev, float* pred_x0, int64_t batch, int64_t n, float cfg_scale,
+                     float guidance_rescale, float temperature, const float* tables,
+                     int32_t* step_index, int32_t advance, void* ws, size_t ws_bytes,
+                     pb_stream_t stream) {
+  return pb_ddim_cfg3_step(x, v_cond, v_uncond, nullptr, noise, x_prev, pred_x0, batch, n, cfg_scale, 0.f,
+                           guidance_rescale, temperature, tables, step_index, advance, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

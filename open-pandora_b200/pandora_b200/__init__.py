@@ -12,15 +12,16 @@ import sys
 
 from . import abi, config  # noqa: F401
 from .diffusion import DiffusionWrapper, LatentDiffusionLite  # noqa: F401
-from .sampler import DDIMSampler  # noqa: F401
+from .sampler import DDIMSampler, DDIMSampler_multicond  # noqa: F401
 from .unet import UNetModel  # noqa: F401
 from .vae import AutoencoderKL, swap_vae_decoder  # noqa: F401
 
-__all__ = ["UNetModel", "DDIMSampler", "LatentDiffusionLite", "DiffusionWrapper", "AutoencoderKL", "install",
+__all__ = ["UNetModel", "DDIMSampler", "DDIMSampler_multicond", "LatentDiffusionLite", "DiffusionWrapper", "AutoencoderKL", "install",
            "swap_unet", "swap_vae_decoder", "abi", "config"]
 
 _UNET_MODULES = ("lvdm.modules.networks.openaimodel3d", "DynamiCrafter.lvdm.modules.networks.openaimodel3d")
 _DDIM_MODULES = ("lvdm.models.samplers.ddim", "DynamiCrafter.lvdm.models.samplers.ddim")
+_DDIM3_MODULES = ("lvdm.models.samplers.ddim_multiplecond", "DynamiCrafter.lvdm.models.samplers.ddim_multiplecond")
 
 
 def install(strict=False):
@@ -30,10 +31,12 @@ def install(strict=False):
     (DynamiCrafter/utils/utils.py:37-42), so replacing the attribute on the already-importable
     reference modules is enough for `target: lvdm.modules.networks.openaimodel3d.UNetModel`
     (configs/inference_512_v1.0.yaml:25).  `model.py` binds `DDIMSampler` by name at import
-    (`model.py:448`), so an already-imported `model` module is patched as well.
+    (`model.py:448`) and the three-branch class as `DDIMSampler_multicond` (`model.py:449`), so an
+    already-imported `model` module is patched as well.
     Returns the list of patched module names."""
     patched = []
-    for names, attr, obj in ((_UNET_MODULES, "UNetModel", UNetModel), (_DDIM_MODULES, "DDIMSampler", DDIMSampler)):
+    for names, attr, obj in ((_UNET_MODULES, "UNetModel", UNetModel), (_DDIM_MODULES, "DDIMSampler", DDIMSampler),
+                             (_DDIM3_MODULES, "DDIMSampler", DDIMSampler_multicond)):
         for name in names:
             try:
                 mod = importlib.import_module(name)
@@ -47,6 +50,8 @@ def install(strict=False):
         if name.split(".")[-1] == "model" and getattr(mod, "DDIMSampler", None) is not None \
                 and mod.DDIMSampler is not DDIMSampler and hasattr(mod, "WorldModel"):
             mod.DDIMSampler = DDIMSampler
+            if hasattr(mod, "DDIMSampler_multicond"):
+                mod.DDIMSampler_multicond = DDIMSampler_multicond
             patched.append(name)
     return patched
 

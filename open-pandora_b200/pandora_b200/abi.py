@@ -106,6 +106,8 @@ SYMBOLS = {
                                          C.c_double, _f, _vp, _vp, _vp, _vp]),
     "pb_ddim_ws_bytes": (_sz, [_i64]),
     "pb_ddim_cfg_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _vp, _vp, _i32, _vp, _sz, _vp]),
+    "pb_ddim_cfg3_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _vp, _vp, _i32, _vp,
+                                    _sz, _vp]),
 }
 
 _lib = None
@@ -528,17 +530,22 @@ def rows_to_video(rows, out, b, c, t, hw):
 
 
 def ddim_cfg_step(x, v_cond, v_uncond, noise, x_prev, pred_x0, cfg_scale, guidance_rescale, temperature,
-                  tables, step_index, advance, ws):
+                  tables, step_index, advance, ws, v_uncond_img=None, cfg_img=0.0):
+    """p_sample_ddim after the U-Net calls; `v_uncond_img` selects the three-branch combine of
+    ddim_multiplecond.py:234 (pb_ddim_cfg3_step)."""
     global launches
     b = x.shape[0]
     n = x.numel() // b
     for t_ in (x, v_cond, noise, x_prev, pred_x0):
         assert t_.dtype == torch.float32 and t_.is_contiguous()
-    assert v_uncond is None or (v_uncond.dtype == torch.float32 and v_uncond.is_contiguous())
+    for t_ in (v_uncond, v_uncond_img):
+        assert t_ is None or (t_.dtype == torch.float32 and t_.is_contiguous())
+    assert v_uncond_img is None or v_uncond is not None
     assert tables.dtype == torch.float32 and step_index.dtype == torch.int32
-    _check(load().pb_ddim_cfg_step(x.data_ptr(), v_cond.data_ptr(), _ptr(v_uncond), noise.data_ptr(),
-                                   x_prev.data_ptr(), pred_x0.data_ptr(), b, n, cfg_scale, guidance_rescale,
-                                   temperature, tables.data_ptr(), step_index.data_ptr(), int(advance),
-                                   _ptr(ws), 0 if ws is None else ws.numel() * ws.element_size(), _stream()),
-           "pb_ddim_cfg_step")
-    launches += 2 + (2 if guidance_rescale > 0 and v_uncond is not None else 0)
+    _check(load().pb_ddim_cfg3_step(x.data_ptr(), v_cond.data_ptr(), _ptr(v_uncond), _ptr(v_uncond_img),
+                                    noise.data_ptr(), x_prev.data_ptr(), pred_x0.data_ptr(), b, n, cfg_scale,
+                                    float(cfg_img), guidance_rescale, temperature, tables.data_ptr(),
+                                    step_index.data_ptr(), int(advance), _ptr(ws),
+                                    0 if ws is None else ws.numel() * ws.element_size(), _stream()),
+           "pb_ddim_cfg3_step")
+    launches += 1 + int(bool(advance)) + (2 if guidance_rescale > 0 and v_uncond is not None else 0)

@@ -98,11 +98,18 @@ class GraphedCFGStep:
     sequence-parallel (batch 1 per rank).  Every operator of the U-Net is per-sample, so this is the same
     arithmetic with half the launches and twice the rows per GEMM."""
 
-    def __init__(self, sampler, unet, shape, cond, uncond, fs, cfg_scale, guidance_rescale, temperature, table):
+    def __init__(self, sampler, unet, shape, cond, uncond, fs, cfg_scale, guidance_rescale, temperature, table,
+                 uncond_img=None, cfg_img=0.0):
         dev = sampler.model.device
         self.unet, self.sampler = unet, sampler
         self.cfg = uncond is not None and cfg_scale != 1.0
         self.cfg_scale, self.rescale, self.temperature = float(cfg_scale), float(guidance_rescale), float(temperature)
+        #: third branch of DDIMSampler_multicond (image conditioning kept, text dropped; ddim_multiplecond.py:232)
+        self.three = self.cfg and uncond_img is not None
+        self.cfg_img = float(cfg_img) if self.three else 0.0
+        if self.three and sampler.cfg_parallel is not None:
+            raise NotImplementedError("CFG-parallel splits two branches over two ranks; the three-branch sampler "
+                                      "runs its branches on one rank (batched) or under sequence parallelism")
         f32 = torch.float32
         b = shape[0]
         self.x = torch.zeros(shape, dtype=f32, device=dev)
@@ -116,74 +123,66 @@ class GraphedCFGStep:
                              or getattr(unet.sequence_parallel, "batch_ok", False)))
         # Every tensor the captured graph reads is OWNED by this object (static addresses): conditioning of a later
         # `sample()` call is copied in (`load`), so one capture serves every round of a rollout.
-        ctx_c, z_c, ctx_u, z_u = self._sources(cond, uncond)
-        nb = 2 * b if self.batched else b
+        srcs = self._sources(cond, uncond, uncond_img if self.three else None)
+        self.n_branch = nbr = (3 if self.three else 2) if self.cfg else 1
+        nb = nbr * b if self.batched else b
         own = lambda t, n: torch.zeros((n, *t.shape[1:]), dtype=t.dtype, device=dev)
         self.ts = torch.zeros((nb,), dtype=torch.long, device=dev)
         self.fs_b = None if fs is None else torch.zeros((nb,), dtype=torch.long, device=dev)
-        if self.batched:
-            self.x2 = torch.zeros((2 * b, *shape[1:]), dtype=f32, device=dev)
-            self.ctx_b, self.z_b = own(ctx_c, 2 * b), own(z_c, 2 * b)
-            self.ctx_c, self.z_c, self.ctx_u, self.z_u = self.ctx_b[:b], self.z_b[:b], self.ctx_b[b:], self.z_b[b:]
+        if self.batched:                       # one buffer, branch k = samples [k*b, (k+1)*b)
+            self.x2 = torch.zeros((nb, *shape[1:]), dtype=f32, device=dev)
+            self.ctx_b, self.z_b = own(srcs[0][0], nb), own(srcs[0][1], nb)
+            self.branches = [(self.ctx_b[k * b:(k + 1) * b], self.z_b[k * b:(k + 1) * b]) for k in range(nbr)]
         else:
-            self.ctx_c, self.z_c = own(ctx_c, b), own(z_c, b)
-            self.ctx_u = self.z_u = None
-            if self.cfg:
-                self.ctx_u, self.z_u = own(ctx_u, b), own(z_u, b)
+            self.branches = [(own(srcs[k][0], b), own(srcs[k][1], b)) for k in range(nbr)]
         self.graph = None
         self.launches_per_step = 0
-        self.load(cond, uncond, fs, table)
+        self.load(cond, uncond, fs, table, uncond_img)
 
     @staticmethod
-    def _sources(cond, uncond):
+    def _sources(cond, uncond, uncond_img=None):
+        """[(context, c_concat)] per branch: conditional, unconditional, image-only."""
         cat = lambda c: c[0] if len(c) == 1 else torch.cat(list(c), 1)
-        ctx_c, z_c = cat(cond["c_crossattn"]), cat(cond["c_concat"])
-        ctx_u = z_u = None
-        if uncond is not None:
-            ctx_u, z_u = cat(uncond["c_crossattn"]), cat(uncond["c_concat"])
-        return ctx_c, z_c, ctx_u, z_u
+        return [(cat(c["c_crossattn"]), cat(c["c_concat"])) for c in (cond, uncond, uncond_img) if c is not None]
 
     def signature(self):
         """What a later call must match to reuse this capture (shapes / dtypes of everything the graph reads)."""
-        sig = lambda t: None if t is None else (tuple(t.shape), t.dtype)
+        sig = lambda t: (tuple(t.shape), t.dtype)
         return (tuple(self.x.shape), self.cfg, self.cfg_scale, self.rescale, self.temperature, tuple(self.table.shape),
-                sig(self.ctx_c), sig(self.z_c), sig(self.ctx_u), sig(self.z_u), self.fs_b is None, self.batched)
+                self.cfg_img, tuple((sig(c), sig(z)) for c, z in self.branches), self.fs_b is None, self.batched)
 
-    def load(self, cond, uncond, fs, table):
+    def load(self, cond, uncond, fs, table, uncond_img=None):
         """Copy the conditioning / schedule of a `sample()` call into the static buffers (host or device sources)
         and, once captured, recompute the cached context K|V projections in place."""
-        ctx_c, z_c, ctx_u, z_u = self._sources(cond, uncond)
+        srcs = self._sources(cond, uncond if self.cfg else None, uncond_img if self.three else None)
         self.table.copy_(table.flip(0), non_blocking=True)
-        self.ctx_c.copy_(ctx_c, non_blocking=True)
-        self.z_c.copy_(z_c, non_blocking=True)
-        if self.cfg:
-            self.ctx_u.copy_(ctx_u, non_blocking=True)
-            self.z_u.copy_(z_u, non_blocking=True)
+        for (ctx, z), (ctx_s, z_s) in zip(self.branches, srcs):
+            ctx.copy_(ctx_s, non_blocking=True)
+            z.copy_(z_s, non_blocking=True)
         if self.fs_b is not None:
             b = self.x.shape[0]
-            self.fs_b[:b].copy_(fs, non_blocking=True)
-            if self.batched:
-                self.fs_b[b:].copy_(fs, non_blocking=True)
+            for k in range(self.fs_b.shape[0] // b):
+                self.fs_b[k * b:(k + 1) * b].copy_(fs, non_blocking=True)
         if self.graph is not None:
             self.refresh_conditioning()
 
     def _body(self):
         cfgp = self.sampler.cfg_parallel if self.cfg else None
-        if self.batched:                       # both branches in one forward over 2b samples
-            b = self.x.shape[0]
+        b = self.x.shape[0]
+        if self.batched:                       # all branches in one forward over n_branch * b samples
             flat = self.x.view(b, -1)
-            abi.copy_rows(flat, self.x2.view(2 * b, -1)[:b])
-            abi.copy_rows(flat, self.x2.view(2 * b, -1)[b:])
+            for k in range(self.n_branch):
+                abi.copy_rows(flat, self.x2.view(self.n_branch * b, -1)[k * b:(k + 1) * b])
             v = self.unet(self.x2, self.ts, context=self.ctx_b, fs=self.fs_b, x_concat=[self.z_b])
-            v_c, v_u = v[:b], v[b:]
+            vs = [v[k * b:(k + 1) * b] for k in range(self.n_branch)]
         elif cfgp is not None:                 # one branch per rank, then all-gather v
-            ctx, z = cfgp.my_branch((self.ctx_c, self.z_c), (self.ctx_u, self.z_u))
-            v_c, v_u = cfgp.exchange(self.unet(self.x, self.ts, context=ctx, fs=self.fs_b, x_concat=[z]))
+            ctx, z = cfgp.my_branch(*self.branches)
+            vs = list(cfgp.exchange(self.unet(self.x, self.ts, context=ctx, fs=self.fs_b, x_concat=[z])))
         else:
-            v_c = self.unet(self.x, self.ts, context=self.ctx_c, fs=self.fs_b, x_concat=[self.z_c])
-            v_u = self.unet(self.x, self.ts, context=self.ctx_u, fs=self.fs_b, x_concat=[self.z_u]) if self.cfg else None
-        abi.ddim_cfg_step(self.x, v_c, v_u, self.noise, self.x, self.pred_x0, self.cfg_scale, self.rescale,
-                          self.temperature, self.table, self.step_index, True, self.ws)
+            vs = [self.unet(self.x, self.ts, context=ctx, fs=self.fs_b, x_concat=[z]) for ctx, z in self.branches]
+        vs += [None] * (3 - len(vs))
+        abi.ddim_cfg_step(self.x, vs[0], vs[1], self.noise, self.x, self.pred_x0, self.cfg_scale, self.rescale,
+                          self.temperature, self.table, self.step_index, True, self.ws, vs[2], self.cfg_img)
 
     def capture(self):
         # eager warm-up on a side stream (fills weight packs / context K,V caches, configures kernels)
@@ -217,9 +216,8 @@ class GraphedCFGStep:
         if self.batched:
             self.unet.refresh_context(self.ctx_b, self.x.shape[2])
             return
-        for ctx in (self.ctx_c, self.ctx_u):
-            if ctx is not None:
-                self.unet.refresh_context(ctx, self.x.shape[2])
+        for ctx, _ in self.branches:
+            self.unet.refresh_context(ctx, self.x.shape[2])
 
     def reset(self, x_T):
         self.x.copy_(x_T)
@@ -456,21 +454,25 @@ class DDIMSampler(object):
         # The capture is cached on the U-Net (a DDIMSampler is constructed per call, model.py:705): later calls
         # with the same shapes and settings copy their conditioning into the static buffers and replay.
         cfg = uc is not None and cfg_scale != 1.0
+        uc_img, cfg_img = self._third_branch(kwargs, cfg_scale)
         if not cfg:
-            uc = None
+            uc = uc_img = None
+        if uc_img is not None and not isinstance(uc_img, dict):
+            return None
         cache = unet._graph_cache
+        sig = lambda t: (tuple(t.shape), t.dtype)
+        want = (tuple(shape), cfg, float(cfg_scale), float(guidance_rescale), float(temperature), tuple(table.shape),
+                float(cfg_img) if uc_img is not None else 0.0,
+                tuple((sig(c), sig(z)) for c, z in GraphedCFGStep._sources(cond, uc, uc_img)), fs is None)
         for g in cache:
-            if (g.sampler_key == self._graph_key() and g.signature()[:6] == (
-                    tuple(shape), cfg, float(cfg_scale), float(guidance_rescale), float(temperature), tuple(table.shape))):
-                try_sig = GraphedCFGStep._sources(cond, uc)
-                sig = lambda t: None if t is None else (tuple(t.shape), t.dtype)
-                if tuple(sig(t) for t in try_sig) == g.signature()[6:10] and (fs is None) == (g.fs_b is None):
-                    g.sampler = self
-                    g.load(cond, uc, fs, table)
-                    cache.remove(g)
-                    cache.append(g)
-                    return g
-        g = GraphedCFGStep(self, unet, tuple(shape), cond, uc, fs, cfg_scale, guidance_rescale, temperature, table)
+            if g.sampler_key == self._graph_key() and g.signature()[:9] == want:
+                g.sampler = self
+                g.load(cond, uc, fs, table, uc_img)
+                cache.remove(g)
+                cache.append(g)
+                return g
+        g = GraphedCFGStep(self, unet, tuple(shape), cond, uc, fs, cfg_scale, guidance_rescale, temperature, table,
+                           uc_img, cfg_img)
         g.sampler_key = self._graph_key()
         g.capture()
         cache.append(g)
@@ -485,6 +487,10 @@ class DDIMSampler(object):
         return (self.batch_cfg, id(self.cfg_parallel) if self.cfg_parallel is not None else None,
                 id(unet.sequence_parallel) if unet.sequence_parallel is not None else None,
                 unet.compute_mode, unet.kernel_impl, p0.dtype, str(p0.device))
+
+    def _third_branch(self, kwargs, cfg_scale):
+        """(conditioning of a third guidance branch or None, its scale): none in the two-branch sampler."""
+        return None, 0.0
 
     def _sync_noise(self, noise):
         if self.replica_group is not None:
@@ -517,23 +523,24 @@ class DDIMSampler(object):
         return (self.batch_cfg and unet is not None and isinstance(c, dict) and isinstance(uc, dict)
                 and (unet.sequence_parallel is None or getattr(unet.sequence_parallel, "batch_ok", False)))
 
-    def _denoise_cfg_batched(self, x32, t, c, uc, **kwargs):
-        """Both CFG branches as one forward over 2b samples (rows [0,b) cond, [b,2b) uncond).  The concatenated
-        conditioning is cached per (cond, uncond) tensor identity so the U-Net's context K/V cache keeps hitting."""
+    def _denoise_cfg_batched(self, x32, t, conds, **kwargs):
+        """All CFG branches as one forward over len(conds)*b samples (branch k = rows [k*b, (k+1)*b)).  The
+        concatenated conditioning is cached per tensor identity so the U-Net's context K/V cache keeps hitting."""
         cat = lambda ts: ts[0] if len(ts) == 1 else torch.cat(list(ts), 1)
-        srcs = (cat(c["c_crossattn"]), cat(uc["c_crossattn"]), cat(c["c_concat"]), cat(uc["c_concat"]))
+        n = len(conds)
+        srcs = tuple(cat(c["c_crossattn"]) for c in conds) + tuple(cat(c["c_concat"]) for c in conds)
         key = tuple((s.data_ptr(), s._version, tuple(s.shape)) for s in srcs)
         if self._cfg_cat is None or self._cfg_cat[0] != key:
-            self._cfg_cat = (key, torch.cat(srcs[:2], 0).contiguous(), torch.cat(srcs[2:], 0).contiguous(), srcs)
+            self._cfg_cat = (key, torch.cat(srcs[:n], 0).contiguous(), torch.cat(srcs[n:], 0).contiguous(), srcs)
         _, ctx_b, z_b, _ = self._cfg_cat
         b = x32.shape[0]
         kw = dict(kwargs)
         fs = kw.get("fs")
         if isinstance(fs, torch.Tensor) and fs.dim() and fs.shape[0] == b:
-            kw["fs"] = torch.cat([fs, fs], 0)
-        v = self._native_unet()(torch.cat([x32, x32], 0), torch.cat([t, t], 0), context=ctx_b, x_concat=[z_b], **kw)
+            kw["fs"] = torch.cat([fs] * n, 0)
+        v = self._native_unet()(torch.cat([x32] * n, 0), torch.cat([t] * n, 0), context=ctx_b, x_concat=[z_b], **kw)
         v = v.float()
-        return v[:b].contiguous(), v[b:].contiguous()
+        return [v[k * b:(k + 1) * b].contiguous() for k in range(n)]
 
     @torch.no_grad()
     def p_sample_ddim(self, x, c, t, index, repeat_noise=False, use_original_steps=False,
@@ -551,16 +558,25 @@ class DDIMSampler(object):
         cfg = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.)
         if cfg and not isinstance(c, (torch.Tensor, dict)):
             raise NotImplementedError
-        v_u = None
+        v_u = v_ui = None
+        uc_img, cfg_img = self._third_branch(kwargs, unconditional_guidance_scale)
+        kwargs = {k: v for k, v in kwargs.items() if k not in ("unconditional_conditioning_img_nonetext", "cfg_img")}
+        if not cfg:
+            uc_img = None
         if cfg and self.cfg_parallel is not None:
+            if uc_img is not None:
+                raise NotImplementedError("CFG-parallel splits two branches; the three-branch sampler does not use it")
             mine = self.cfg_parallel.my_branch(c, unconditional_conditioning)
             v_c, v_u = self.cfg_parallel.exchange(self._denoise(x32, t, mine, **kwargs).float().contiguous())
-        elif cfg and self._can_batch_cfg(c, unconditional_conditioning):
-            v_c, v_u = self._denoise_cfg_batched(x32, t, c, unconditional_conditioning, **kwargs)
+        elif cfg and self._can_batch_cfg(c, unconditional_conditioning) and isinstance(uc_img, (dict, type(None))):
+            conds = [c, unconditional_conditioning] + ([uc_img] if uc_img is not None else [])
+            v_c, v_u, v_ui = (self._denoise_cfg_batched(x32, t, conds, **kwargs) + [None])[:3]
         else:
             v_c = self._denoise(x32, t, c, **kwargs).float().contiguous()
             if cfg:
                 v_u = self._denoise(x32, t, unconditional_conditioning, **kwargs).float().contiguous()
+            if uc_img is not None:
+                v_ui = self._denoise(x32, t, uc_img, **kwargs).float().contiguous()
         shape = x.shape
         if repeat_noise:
             noise = torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
@@ -574,7 +590,8 @@ class DDIMSampler(object):
         x_prev, pred_x0 = torch.empty_like(x32), torch.empty_like(x32)
         ws = torch.empty(4 * shape[0], dtype=torch.float64, device=device) if (cfg and guidance_rescale > 0) else None
         abi.ddim_cfg_step(x32, v_c, v_u, noise.contiguous(), x_prev, pred_x0, float(unconditional_guidance_scale),
-                          float(guidance_rescale), float(temperature), table, idx[index:index + 1], False, ws)
+                          float(guidance_rescale), float(temperature), table, idx[index:index + 1], False, ws,
+                          v_ui, float(cfg_img))
         if quantize_denoised:
             # off the Open-Pandora path (VQ first stage); x_prev is then rebuilt from the quantised x0
             raise NotImplementedError("quantize_denoised needs a VQ first stage, which this path does not have")
@@ -611,3 +628,26 @@ class DDIMSampler(object):
             noise = torch.randn_like(x0)
         shp = (t.shape[0],) + (1,) * (x0.dim() - 1)
         return sqrt_ac.gather(-1, t).reshape(shp) * x0 + sqrt_omac.gather(-1, t).reshape(shp) * noise
+
+
+class DDIMSampler_multicond(DDIMSampler):
+    """Three-branch guidance (text + image) — mirror of lvdm/models/samplers/ddim_multiplecond.py `DDIMSampler`,
+    the class `model.py:705` picks when `multiple_cond_cfg=True`.
+
+    Per step the reference evaluates the U-Net on the conditional, the unconditional and the "image kept, text
+    dropped" conditioning (`kwargs['unconditional_conditioning_img_nonetext']`, :226, a KeyError when absent) and
+    combines  v = v_u + cfg_img*(v_ui - v_u) + s*(v_c - v_ui)  (:234; cfg_img defaults to s, :222-223); everything
+    after that is the two-branch step.  Here the three forwards run as ONE forward over 3b samples inside the
+    captured graph and the combine is part of the fused update kernel (`pb_ddim_cfg3_step`).
+
+    Schedule: the reference's `make_schedule` (:24-58) differs from ddim.py's only in casting the (unused here)
+    DDPM buffers to bf16, and it calls `np.sqrt(alphas_cumprod.cpu())` on the model's bf16 buffer
+    (ddpm3d.py:139-142), which raises TypeError under numpy — the class only runs on a model whose schedule
+    buffers were cast to fp32 (`model.float()`), where its DDIM tables are identical to ddim.py's.  This mirror
+    therefore uses the parent's fp32 schedule; parity is pinned against the reference class run that way
+    (tests/golden/ddim_multicond_*.npz)."""
+
+    def _third_branch(self, kwargs, cfg_scale):
+        uc_img = kwargs["unconditional_conditioning_img_nonetext"]          # KeyError like the reference (:226)
+        cfg_img = kwargs.get("cfg_img")
+        return uc_img, (cfg_scale if cfg_img is None else cfg_img)

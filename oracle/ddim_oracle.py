@@ -92,15 +92,21 @@ def rescale_noise_cfg(cfg_out, cond_out, phi):
 
 
 def ddim_step(buf, tab, x, v_cond, v_uncond, step, index, noise, cfg_scale=1.0,
-              guidance_rescale=0.0, temperature=1.0):
-    """ddim.py:218-290 for parameterization 'v'. All tensor arithmetic happens in x.dtype."""
+              guidance_rescale=0.0, temperature=1.0, v_uncond_img=None, cfg_img=None):
+    """ddim.py:218-290 for parameterization 'v'. All tensor arithmetic happens in x.dtype.
+    With `v_uncond_img` it is ddim_multiplecond.py:211-283 (three-branch combine :234, cfg_img defaults to the
+    text scale :222-223); the rest of that function is the same arithmetic."""
     b, dt = x.shape[0], x.dtype
     shp = (b,) + (1,) * (x.dim() - 1)
     full = lambda val: torch.full(shp, val, dtype=dt, device=x.device)
     if v_uncond is None or cfg_scale == 1.0:
         v = v_cond
     else:
-        v = v_uncond + cfg_scale * (v_cond - v_uncond)
+        if v_uncond_img is None:
+            v = v_uncond + cfg_scale * (v_cond - v_uncond)
+        else:
+            s_img = cfg_scale if cfg_img is None else cfg_img
+            v = v_uncond + s_img * (v_uncond_img - v_uncond) + cfg_scale * (v_cond - v_uncond_img)
         if guidance_rescale > 0.0:
             v = rescale_noise_cfg(v, v_cond, guidance_rescale)
     t = torch.full((b,), int(step), dtype=torch.long, device=x.device)
@@ -119,8 +125,8 @@ def ddim_step(buf, tab, x, v_cond, v_uncond, step, index, noise, cfg_scale=1.0,
 @torch.no_grad()
 def ddim_sample(unet_fn, buf, x_T, cond, uncond, S=50, spacing="uniform_trailing", eta=1.0,
                 cfg_scale=7.5, guidance_rescale=0.0, fs=None, noises=None, precision=None,
-                record=None):
-    """ddim.py:141-215.  `unet_fn(xc, t, context, fs)` is the denoiser;
+                record=None, uncond_img=None, cfg_img=None):
+    """ddim.py:141-215 (and, with `uncond_img`, ddim_multiplecond.py:136-208: third forward per step).  `unet_fn(xc, t, context, fs)` is the denoiser;
     cond/uncond = dict(c_crossattn=[ctx], c_concat=[z]) (hybrid conditioning, ddpm3d.py:1077-1081).
     `noises[i]` is the N(0,1) draw of loop iteration i (the reference calls torch.randn each step)."""
     tab = ddim_tables(buf, S, spacing, eta)
@@ -139,8 +145,10 @@ def ddim_sample(unet_fn, buf, x_T, cond, uncond, S=50, spacing="uniform_trailing
         index = S - i - 1
         v_c = apply(cond)
         v_u = apply(uncond) if (uncond is not None and cfg_scale != 1.0) else None
+        v_ui = apply(uncond_img) if (v_u is not None and uncond_img is not None) else None
         noise = noises[i] if noises is not None else torch.randn(x.shape, device=x.device)
         if record is not None:
             record.append(dict(x=x, v_c=v_c, v_u=v_u))
-        x, pred_x0 = ddim_step(buf, tab, x, v_c, v_u, step, index, noise, cfg_scale, guidance_rescale)
+        x, pred_x0 = ddim_step(buf, tab, x, v_c, v_u, step, index, noise, cfg_scale, guidance_rescale,
+                               v_uncond_img=v_ui, cfg_img=cfg_img)
     return x, pred_x0

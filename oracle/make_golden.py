@@ -86,9 +86,16 @@ def unet_case(name, params, latent, per_frame_image, seed_w, seed_x, tval, fs):
     return ref
 
 
-def sampler_case(name, params, dparams, latent, S, cfg_scale, rescale, seed_w, seed_x, spacing, eta):
+def sampler_case(name, params, dparams, latent, S, cfg_scale, rescale, seed_w, seed_x, spacing, eta,
+                 multicond=False, cfg_img=None):
+    """`multicond`: the three-branch class (ddim_multiplecond.py).  Its make_schedule calls numpy on the model's
+    bf16 schedule buffers (:40, TypeError), so the reference is run the only way it can run: on `model.float()`
+    (same buffer VALUES, fp32 containers); the DDIM tables are then identical to ddim.py's."""
     from lvdm.models.ddpm3d import LatentVisualDiffusion
-    from lvdm.models.samplers.ddim import DDIMSampler
+    if multicond:
+        from lvdm.models.samplers.ddim_multiplecond import DDIMSampler
+    else:
+        from lvdm.models.samplers.ddim import DDIMSampler
     ident = {"target": "torch.nn.Identity"}
     unet_config = AttrDict(target="lvdm.modules.networks.openaimodel3d.UNetModel",
                            params=dict(params, use_checkpoint=False))
@@ -109,17 +116,35 @@ def sampler_case(name, params, dparams, latent, S, cfg_scale, rescale, seed_w, s
     inp = synth_inputs(1, latent, params["context_dim"], seed_x)
     cond = dict(c_crossattn=[inp["context"]], c_concat=[inp["c_concat"]])
     uc = dict(c_crossattn=[inp["uc_context"]], c_concat=[inp["c_concat"]])
+    uc_img = None
+    if multicond:
+        # "image kept, text dropped" (inference.py:196-203): the empty-prompt text tokens followed by the image tokens
+        n_txt = 77
+        uc_img = dict(c_crossattn=[torch.cat([inp["uc_context"][:, :n_txt], inp["context"][:, n_txt:]], 1)],
+                      c_concat=[inp["c_concat"]])
+        try:
+            DDIMSampler(model).make_schedule(S, spacing, eta, verbose=False)
+            raise AssertionError("the reference's multicond make_schedule was expected to fail on bf16 buffers")
+        except TypeError as e:
+            print(f"[ddim:{name}] reference make_schedule on the bf16 schedule: TypeError: {e}")
+        model_buffers_bf16 = {k: getattr(model, k).clone() for k in
+                              ("alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "scale_arr")}
+        model.float()
+        sampler = DDIMSampler(model)
     fs = torch.tensor([params["default_fs"]], dtype=torch.long)
     torch.manual_seed(seed_x + 99)
     samples, inter = sampler.sample(
         S=S, batch_size=1, shape=latent, conditioning=cond, unconditional_conditioning=uc,
         unconditional_guidance_scale=cfg_scale, eta=eta, x_T=inp["x"], fs=fs, verbose=False,
-        timestep_spacing=spacing, guidance_rescale=rescale, cfg_img=None, round_info=(1, 1),
-        gr_progress_bar=None, unconditional_conditioning_img_nonetext=None)
+        timestep_spacing=spacing, guidance_rescale=rescale, cfg_img=cfg_img, round_info=(1, 1),
+        gr_progress_bar=None, unconditional_conditioning_img_nonetext=uc_img)
     # ---- oracle arm: same seeds, same draw order
     buf = ddim_oracle.model_schedule(**dparams)
     for k in ("alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "scale_arr"):
-        assert torch.equal(buf[k], getattr(model, k)), k
+        if multicond:
+            assert torch.equal(buf[k], model_buffers_bf16[k]) and torch.equal(buf[k].float(), getattr(model, k)), k
+        else:
+            assert torch.equal(buf[k], getattr(model, k)), k
     tab = ddim_oracle.ddim_tables(buf, S, spacing, eta)
     assert np.array_equal(tab["timesteps"], sampler.ddim_timesteps)
     for k, ref_v in (("alphas", sampler.ddim_alphas), ("alphas_prev", sampler.ddim_alphas_prev),
@@ -128,7 +153,8 @@ def sampler_case(name, params, dparams, latent, S, cfg_scale, rescale, seed_w, s
     sd = synth_state_dict(unet_oracle.unet_param_shapes(params), seed_w)
     fn = lambda xc, t, cc, fs_: unet_oracle.unet_forward(sd, params, xc, t, cc, fs_)
     torch.manual_seed(seed_x + 99)
-    x_orc, _ = ddim_oracle.ddim_sample(fn, buf, inp["x"], cond, uc, S, spacing, eta, cfg_scale, rescale, fs)
+    x_orc, _ = ddim_oracle.ddim_sample(fn, buf, inp["x"], cond, uc, S, spacing, eta, cfg_scale, rescale, fs,
+                                       uncond_img=uc_img, cfg_img=cfg_img)
     e = rel_l2(x_orc, samples)
     print(f"[ddim:{name}] oracle vs reference final latent rel-L2 = {e:.3e}")
     assert e < 1e-4, e
@@ -142,7 +168,7 @@ def sampler_case(name, params, dparams, latent, S, cfg_scale, rescale, seed_w, s
         sqrt_omac=model.sqrt_one_minus_alphas_cumprod.float().numpy(),
         meta=json.dumps(dict(params=params, dparams=dparams, latent=latent, S=S, cfg_scale=cfg_scale,
                              guidance_rescale=rescale, seed_w=seed_w, seed_x=seed_x, spacing=spacing,
-                             eta=eta, noise_seed=seed_x + 99)))
+                             eta=eta, noise_seed=seed_x + 99, multicond=multicond, cfg_img=cfg_img)))
 
 
 def full_width_case(name="full512", seed_w=1234, seed_x=0, stride=8):
@@ -235,6 +261,15 @@ def main():
         torch.set_num_threads(os.cpu_count())
         vae_case("full_width_8x12", VAE_DDCONFIG, (4, 2, 8, 12), 1234, 0)        # the real decoder, 2 frames, 64 x 96 px
         vae_case("narrow_16x8", dict(VAE_DDCONFIG, ch=64), (4, 3, 16, 8), 77, 3)
+        return
+    if "--multicond" in sys.argv:    # three-branch guidance fixtures
+        os.makedirs(GOLD, exist_ok=True)
+        torch.set_num_threads(os.cpu_count())
+        small = pcfg.small_unet()
+        sampler_case("multicond_s5_img2", small, pcfg.DIFFUSION_512, (4, 16, 8, 8), 5, 7.5, 0.7, 1234, 6,
+                     "uniform_trailing", 1.0, multicond=True, cfg_img=2.0)
+        sampler_case("multicond_s4_default", small, pcfg.DIFFUSION_1024, (4, 16, 8, 8), 4, 5.0, 0.0, 99, 7,
+                     "uniform_trailing", 0.0, multicond=True, cfg_img=None)
         return
     if "--full" in sys.argv:         # ~15 min of CPU: the full-width fixture only
         os.makedirs(GOLD, exist_ok=True)

@@ -13,6 +13,14 @@ from pandora_b200.synthetic import synth_inputs, synth_state_dict
 
 UNET_CASES = ["unet_small_perframe", "unet_small_t499_nofs", "unet_small_sharedimg", "unet_small_b2ish"]
 DDIM_CASES = ["ddim_s5_cfg75", "ddim_s8_cfg75_r07", "ddim_s4_eta0", "ddim_s50_cfg75_r07"]
+#: three-branch guidance, produced by the reference's ddim_multiplecond.DDIMSampler (make_golden.py --multicond)
+MULTICOND_CASES = ["ddim_multicond_s5_img2", "ddim_multicond_s4_default"]
+
+
+def image_only_conditioning(inp, n_text=77):
+    """"image kept, text dropped" conditioning of the third branch, as make_golden.py built it."""
+    return dict(c_crossattn=[torch.cat([inp["uc_context"][:, :n_text], inp["context"][:, n_text:]], 1)],
+                c_concat=[inp["c_concat"]])
 
 
 def unet_case_inputs(meta):
@@ -87,7 +95,7 @@ def test_timestep_embedding_uses_bf16_table():
     assert float((e - e32).abs().max()) > 0.5          # the bf16 table really matters
 
 
-@pytest.mark.parametrize("name", DDIM_CASES)
+@pytest.mark.parametrize("name", DDIM_CASES + MULTICOND_CASES)
 def test_ddim_oracle_matches_reference_golden(name):
     z, meta = load_golden(name)
     p, dp = meta["params"], meta["dparams"]
@@ -104,8 +112,10 @@ def test_ddim_oracle_matches_reference_golden(name):
     fs = torch.tensor([p["default_fs"]], dtype=torch.long)
     fn = lambda xc, t, cc, fs_: unet_oracle.unet_forward(sd, p, xc, t, cc, fs_)
     torch.manual_seed(meta["noise_seed"])
+    uc_img = image_only_conditioning(inp) if meta.get("multicond") else None
     x, x0 = ddim_oracle.ddim_sample(fn, buf, inp["x"], cond, uc, meta["S"], meta["spacing"], meta["eta"],
-                                    meta["cfg_scale"], meta["guidance_rescale"], fs)
+                                    meta["cfg_scale"], meta["guidance_rescale"], fs, uncond_img=uc_img,
+                                    cfg_img=meta.get("cfg_img"))
     assert rel_l2(x, z["samples"]) < 1e-4
     assert rel_l2(x0, z["pred_x0"]) < 1e-4
 

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from helpers import load_golden, psnr, rel_l2
-from test_oracle_golden import DDIM_CASES, UNET_CASES, unet_case_inputs
+from test_oracle_golden import DDIM_CASES, MULTICOND_CASES, UNET_CASES, image_only_conditioning, unet_case_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -98,17 +98,19 @@ def test_cpu_input_fails_loudly():
         m(torch.zeros(1, 8, 16, 8, 8), torch.zeros(1, dtype=torch.long), context=torch.zeros(1, 333, 128))
 
 
-def _sampler_run(meta, dtype, mode=None):
-    from pandora_b200 import DDIMSampler, LatentDiffusionLite
+def _sampler_run(meta, dtype, mode=None, graph=True, batch_cfg=True):
+    from pandora_b200 import DDIMSampler, DDIMSampler_multicond, LatentDiffusionLite
     from pandora_b200.synthetic import synth_inputs
     p, dp = meta["params"], meta["dparams"]
     unet = native_unet(p, meta["seed_w"], dtype)
     unet.compute_mode = mode
     model = LatentDiffusionLite(unet, **dp).cuda()
-    sampler = DDIMSampler(model)
+    sampler = (DDIMSampler_multicond if meta.get("multicond") else DDIMSampler)(model)
+    sampler.use_cuda_graph, sampler.batch_cfg = graph, batch_cfg
     inp = {k: v.cuda() for k, v in synth_inputs(1, tuple(meta["latent"]), p["context_dim"], meta["seed_x"]).items()}
     cond = dict(c_crossattn=[inp["context"]], c_concat=[inp["c_concat"]])
     uc = dict(c_crossattn=[inp["uc_context"]], c_concat=[inp["c_concat"]])
+    uc_img = image_only_conditioning(inp) if meta.get("multicond") else None
     fs = torch.tensor([p["default_fs"]], dtype=torch.long, device="cuda")
     # the golden run drew its noise from the CPU generator; replay the identical draws
     torch.manual_seed(meta["noise_seed"])
@@ -121,12 +123,44 @@ def _sampler_run(meta, dtype, mode=None):
             S=meta["S"], batch_size=1, shape=tuple(meta["latent"]), conditioning=cond,
             unconditional_conditioning=uc, unconditional_guidance_scale=meta["cfg_scale"], eta=meta["eta"],
             x_T=inp["x"], fs=fs, verbose=False, timestep_spacing=meta["spacing"],
-            guidance_rescale=meta["guidance_rescale"], cfg_img=None, round_info=(1, 1), gr_progress_bar=None,
-            unconditional_conditioning_img_nonetext=None,
+            guidance_rescale=meta["guidance_rescale"], cfg_img=meta.get("cfg_img"), round_info=(1, 1),
+            gr_progress_bar=None, unconditional_conditioning_img_nonetext=uc_img,
             precision=torch.bfloat16 if dtype == torch.bfloat16 else None)
     finally:
         torch.randn = orig
     return sampler, samples, inter
+
+
+@pytest.mark.parametrize("graph,batch_cfg", [(True, True), (True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("name", MULTICOND_CASES)
+def test_multicond_sampler_fp32_matches_reference_golden(name, graph, batch_cfg):
+    """Three-branch guidance (ddim_multiplecond.py:226-236) against the reference class's own output: captured
+    graph / eager loop, three forwards batched as one or run one after the other."""
+    z, meta = load_golden(name)
+    sampler, samples, inter = _sampler_run(meta, torch.float32, graph=graph, batch_cfg=batch_cfg)
+    assert np.array_equal(np.asarray([float(v) for v in sampler.ddim_sigmas]), z["sigmas"])
+    e = rel_l2(samples, z["samples"])
+    print(f"{name} graph={graph} batched={batch_cfg}: fp32 final latent rel-L2 = {e:.3e}")
+    assert e < FP32_TOL
+    assert rel_l2(inter["pred_x0"][-1], z["pred_x0"]) < FP32_TOL
+
+
+def test_multicond_sampler_requires_the_third_conditioning():
+    from pandora_b200 import DDIMSampler_multicond
+    z, meta = load_golden(MULTICOND_CASES[0])
+    import test_unet_gpu as me
+    orig = me.image_only_conditioning
+    with pytest.raises(KeyError):                   # kwargs['unconditional_conditioning_img_nonetext'], :226
+        from pandora_b200 import LatentDiffusionLite
+        from pandora_b200.synthetic import synth_inputs
+        p = meta["params"]
+        model = LatentDiffusionLite(native_unet(p, 1, torch.float32), **meta["dparams"]).cuda()
+        inp = {k: v.cuda() for k, v in synth_inputs(1, tuple(meta["latent"]), p["context_dim"], 0).items()}
+        cond = dict(c_crossattn=[inp["context"]], c_concat=[inp["c_concat"]])
+        DDIMSampler_multicond(model).sample(S=2, batch_size=1, shape=tuple(meta["latent"]), conditioning=cond,
+                                            unconditional_conditioning=cond, unconditional_guidance_scale=2.0,
+                                            x_T=inp["x"], verbose=False, timestep_spacing="uniform_trailing")
+    assert orig is me.image_only_conditioning
 
 
 @pytest.mark.parametrize("name", DDIM_CASES)
