@@ -34,6 +34,23 @@ struct AttP {
   int o_tma;             // single-key-tile kernel: the output leaves as bulk tensor stores through tmO
 };
 
+#ifdef PB_ATT_TRACE
+// Profiling build only (tools/attn_timeline.py): per-phase SM clock stamps of CTA (0,0,0) of tc_attention3_kernel.
+// Layout (int64): [role 0..2][ATT_TRACE_MAX]; role 0 = issuer, 1 / 2 = warp 0 of the softmax group of tile 0 / 1.
+constexpr int ATT_TRACE_MAX = 4096;
+__device__ long long* g_att_trace = nullptr;
+#define ATT_TRACE_DECL(role)                                                                                     \
+  long long* tr_ = (g_att_trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0) ? g_att_trace + (role) * ATT_TRACE_MAX : nullptr; \
+  int tr_n_ = 0;
+#define ATT_TRACE(tag)                                                                          \
+  do {                                                                                          \
+    if (tr_ && tr_n_ < ATT_TRACE_MAX - 1) tr_[tr_n_++] = (clock64() << 8) | (long long)(tag);  \
+  } while (0)
+#else
+#define ATT_TRACE_DECL(role)
+#define ATT_TRACE(tag)
+#endif
+
 // MN-major B operand tile [k rows][64 contiguous n], 128-byte swizzle: 8-row K groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -399,7 +416,8 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   auto o_full = [&](int t) { return bars + 8u * (7 + 2 * V3_STAGES + t); };
   const uint32_t tmem_slot = bars + 8u * V3_NBARS;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int q_tile0 = blockIdx.x * 2, head = blockIdx.y, n = blockIdx.z;
   const int n_tiles = p.kv_tiles;
 
@@ -440,57 +458,76 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN);
-      const uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);     // B (= V) MN-major
-      int s_iss[2] = {0, 0}, pv_iss[2] = {0, 0}, released = 0;
-      uint32_t idle = 0;
-      mbar_wait(q_full, 0);
-      while (pv_iss[0] < n_tiles || pv_iss[1] < n_tiles) {
-        bool did = false;
+    // The WHOLE warp runs the event loop in uniform control flow (`warp` comes from a shuffle, so the compiler
+    // knows it is warp-uniform) and one elected lane issues.  With the loop under `if (lane == 0)` every
+    // tcgen05.mma sat in a compiler-generated election loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~100 clk per
+    // MMA, measured with tools/attn_timeline.py): 24 MMAs per key tile made the ISSUER the bottleneck of the
+    // kernel (3500 clk per key tile against 2050 clk of exponentials).
+    const uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN);
+    const uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);     // B (= V) MN-major
+    int s_iss0 = 0, s_iss1 = 0, pv_iss0 = 0, pv_iss1 = 0, released = 0;
+    uint32_t idle = 0;
+    ATT_TRACE_DECL(0)
+    mbar_wait(q_full, 0);
+    ATT_TRACE(0);
+    const uint64_t q_desc0 = make_smem_desc_sw128(sQ(0)), q_desc1 = make_smem_desc_sw128(sQ(1));
+    while (pv_iss0 < n_tiles || pv_iss1 < n_tiles) {
+      bool did = false;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (s_iss[t] < n_tiles) {
-            // S_t,j overwrites S_t,j-1: the softmax warps must have it in registers; K_j must have landed
-            const int j = s_iss[t], st = j % V3_STAGES;
-            if ((j == 0 || mbar_test(s_free(t), (j - 1) & 1)) && mbar_test(kv_full(st), (j / V3_STAGES) & 1)) {
-              tc_fence_after();
-              const uint64_t q_desc = make_smem_desc_sw128(sQ(t));
+      for (int t = 0; t < 2; ++t) {
+        int& s_iss = t ? s_iss1 : s_iss0;
+        int& pv_iss = t ? pv_iss1 : pv_iss0;
+        if (s_iss < n_tiles) {
+          // S_t,j overwrites S_t,j-1: the softmax warps must have it in registers; K_j must have landed
+          const int j = s_iss, st = j % V3_STAGES;
+          if ((j == 0 || mbar_test(s_free(t), (j - 1) & 1)) && mbar_test(kv_full(st), (j / V3_STAGES) & 1)) {
+            tc_fence_after();
+            ATT_TRACE(5);
+            if (elect_one()) {
+              const uint64_t q_desc = t ? q_desc1 : q_desc0;
               const uint64_t k_desc = make_smem_desc_sw128(sK(st));
               const uint32_t d = tmem_base + (uint32_t)t * ATT_BN;
 #pragma unroll
               for (int k = 0; k < ATT_D / UMMA_K; ++k) umma_bf16(d, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
               umma_commit(s_full(t));
-              ++s_iss[t];
-              did = true;
             }
+            __syncwarp();
+            ATT_TRACE(1 + t);
+            ++s_iss;
+            did = true;
           }
-          if (pv_iss[t] < s_iss[t]) {
-            const int j = pv_iss[t], st = j % V3_STAGES;
-            if (mbar_test(p_full(t), j & 1)) {   // P_t,j is in tensor memory, O_t has been rescaled if it had to be
-              tc_fence_after();
+        }
+        if (pv_iss < s_iss) {
+          const int j = pv_iss, st = j % V3_STAGES;
+          if (mbar_test(p_full(t), j & 1)) {   // P_t,j is in tensor memory, O_t has been rescaled if it had to be
+            tc_fence_after();
+            ATT_TRACE(6);
+            ++pv_iss;
+            // K_j / V_j are free once both query tiles have issued every product on them
+            const int lo = pv_iss0 < pv_iss1 ? pv_iss0 : pv_iss1;
+            if (elect_one()) {
               const uint32_t d = tmem_base + V3_O_COL0 + (uint32_t)t * ATT_D;
               const uint32_t a_tm = tmem_base + V3_P_COL0 + (uint32_t)t * 64;     // bf16 pairs: 8 columns per k-step
+              const uint64_t b_desc = make_smem_desc_mn_sw128(sV(st));
 #pragma unroll
-              for (int k = 0; k < ATT_BN / UMMA_K; ++k) {
-                const uint64_t b_desc = make_smem_desc_mn_sw128(sV(st) + k * 16 * 128);
-                umma_bf16_ts(d, a_tm + (uint32_t)(k * 8), b_desc, idesc_o, (j | k) != 0);
-              }
+              for (int k = 0; k < ATT_BN / UMMA_K; ++k)                            // 16 keys = 2048 B = 128 desc units
+                umma_bf16_ts(d, a_tm + (uint32_t)(k * 8), b_desc + (uint64_t)(k * 128), idesc_o, (j | k) != 0);
               umma_commit(o_full(t));
-              ++pv_iss[t];
-              // K_j / V_j are free once both query tiles have issued every product on them
-              const int lo = pv_iss[0] < pv_iss[1] ? pv_iss[0] : pv_iss[1];
-              while (released < lo) { umma_commit(kv_empty(released % V3_STAGES)); ++released; }
-              did = true;
+              for (int r = released; r < lo; ++r) umma_commit(kv_empty(r % V3_STAGES));
             }
+            __syncwarp();
+            released = lo > released ? lo : released;
+            ATT_TRACE(3 + t);
+            did = true;
           }
         }
-        if (did) { idle = 0; continue; }
-        if (++idle > (1u << 24)) {
+      }
+      if (did) { idle = 0; continue; }
+      if (++idle > (1u << 24)) {
+        if (lane == 0)
           printf("pandora_b200: attention issuer timeout (block %d,%d,%d s %d/%d pv %d/%d)\n", blockIdx.x, blockIdx.y,
-                 blockIdx.z, s_iss[0], s_iss[1], pv_iss[0], pv_iss[1]);
-          __trap();
-        }
+                 blockIdx.z, s_iss0, s_iss1, pv_iss0, pv_iss1);
+        __trap();
       }
     }
   } else if (warp >= 4) {
@@ -503,12 +540,19 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t p_addr = lane_addr + V3_P_COL0 + (uint32_t)t * 64;
     const uint32_t o_addr = lane_addr + V3_O_COL0 + (uint32_t)t * ATT_D;
     float m_run = -INFINITY, l = 0.f;
+#ifdef PB_ATT_TRACE
+    long long* tr_ = (g_att_trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && quarter == 0 && lane == 0)
+                         ? g_att_trace + (1 + t) * ATT_TRACE_MAX : nullptr;
+    int tr_n_ = 0;
+#endif
 
     for (int j = 0; j < n_tiles; ++j) {
       const int valid = p.nkv - j * ATT_BN;
       const bool full = valid >= ATT_BN;
+      ATT_TRACE(10);
       mbar_wait(s_full(t), j & 1);
       tc_fence_after();
+      ATT_TRACE(11);
       float v[4][32];
       tmem_ld32(s_addr, v[0]);
       tmem_ld32(s_addr + 32, v[1]);
@@ -519,6 +563,7 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free(t));
+      ATT_TRACE(12);
       float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -543,6 +588,8 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       float lq[4] = {0.f, 0.f, 0.f, 0.f};
       const float neg_m = -m_run;
       uint32_t w[4][16];
+      ATT_TRACE(13);
+      ATT_TRACE(14);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (full) {                                       // no per-element key masking on all but the last tile
@@ -564,12 +611,14 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
       }
+      ATT_TRACE(15);
       l += (lq[0] + lq[1]) + (lq[2] + lq[3]);
       if (j > 0) {
         // PV_t,j-1 must be complete before P is overwritten (and before O may be rescaled); it was issued a whole
         // softmax period ago
         mbar_wait(o_full(t), (j - 1) & 1);
         tc_fence_after();
+        ATT_TRACE(16);
         if (rescale) {
 #pragma unroll 1
           for (int c = 0; c < ATT_D; c += 32) {
@@ -588,6 +637,7 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(t));
+      ATT_TRACE(17);
     }
     // ---- epilogue: O_t / l
     mbar_wait(o_full(t), (n_tiles - 1) & 1);
@@ -636,6 +686,13 @@ static int encode_rows3d(CUtensorMap* m, const pb_attn_operand& o, int64_t cols,
 
 }  // namespace tc
 }  // namespace pb
+
+#ifdef PB_ATT_TRACE
+extern "C" int pb_debug_attn_trace(void* device_buffer) {
+  long long* ptr = reinterpret_cast<long long*>(device_buffer);
+  return cudaMemcpyToSymbol(pb::tc::g_att_trace, &ptr, sizeof(ptr)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int pb_tc_attention(const pb_attn_args* a, pb_stream_t stream) {
   using namespace pb;

@@ -143,7 +143,8 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
                                               uint32_t tmem_base, uint32_t epi_base, uint32_t tfull0, uint32_t tempty0,
                                               uint32_t rfull0, int first, int step, int total, int rank) {
   constexpr int NT = num_teams(GEGLU);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // warp-uniform for ptxas
+  const int lane = threadIdx.x & 31;
   const int team = (warp - 2) >> 2;
   const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
   const int r = quarter * 32 + lane;       // accumulator row owned by this thread
@@ -368,7 +369,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t rfull0 = bar_base + 8u * (2 * MAX_STAGES + 4);
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * MAX_SLOTS);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // warp-uniform for ptxas
+  const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.taps * p.k_chunks;
 
@@ -393,8 +395,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ================================================================== TMA producer
-    if (lane == 0) {
+    // ================================================================== TMA producer (uniform loop, elected issue)
+    {
       int stage = 0, phase = 0;
       for (int work = blockIdx.x; work < total_tiles * p.splits; work += gridDim.x) {
         const int tile = work / p.splits, split = work - tile * p.splits;
@@ -409,32 +411,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int it = it0; it < it1; ++it) {
           const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t a_dst = smem_base + stage * stage_bytes;
-          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), (uint32_t)stage_bytes);
-          if (MODE == PB_A_LINEAR) {
-            tma_load_2d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
-          } else if (MODE == PB_A_CONV3X3) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx * p.cstride + kx - 1, cy * p.cstride + ky - 1, cn);
-          } else {
-            tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
+          if (elect_one()) {
+            const uint32_t a_dst = smem_base + stage * stage_bytes;
+            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+            mbar_expect_tx(full_bar(stage), (uint32_t)stage_bytes);
+            if (MODE == PB_A_LINEAR) {
+              tma_load_2d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
+            } else if (MODE == PB_A_CONV3X3) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx * p.cstride + kx - 1, cy * p.cstride + ky - 1, cn);
+            } else {
+              tma_load_4d(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
+            }
+            const int kcol = it * BLOCK_K;   // weight column = tap*Cin + kc*64
+            if (GEGLU) {
+              const int half = p.block_n >> 1;
+              tma_load_2d(b_dst, &tmB, full_bar(stage), kcol, n_tile * half);
+              tma_load_2d(b_dst + half * BLOCK_K * 2, &tmB, full_bar(stage), kcol, p.geglu_half + n_tile * half);
+            } else {
+              tma_load_2d(b_dst, &tmB, full_bar(stage), kcol, n_tile * p.block_n);
+            }
           }
-          const int kcol = it * BLOCK_K;   // weight column = tap*Cin + kc*64
-          if (GEGLU) {
-            const int half = p.block_n >> 1;
-            tma_load_2d(b_dst, &tmB, full_bar(stage), kcol, n_tile * half);
-            tma_load_2d(b_dst + half * BLOCK_K * 2, &tmB, full_bar(stage), kcol, p.geglu_half + n_tile * half);
-          } else {
-            tma_load_2d(b_dst, &tmB, full_bar(stage), kcol, n_tile * p.block_n);
-          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop in uniform control flow (`warp` comes from a shuffle) and one elected lane
+    // issues: under `if (lane == 0)` ptxas wraps EVERY tcgen05.mma in an election loop (ELECT / R2UR.BROADCAST /
+    // BRA.U.ANY, ~100 clk per MMA measured in the attention kernel), which paces the tensor pipe by the issuer.
+    {
       const uint32_t idesc = make_idesc_bf16(BLOCK_M, (uint32_t)p.block_n);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int work = blockIdx.x; work < total_tiles * p.splits; work += gridDim.x) {
@@ -446,18 +454,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int it = it0; it < it1; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-          const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_STAGE_BYTES);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + stage * stage_bytes;
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+            const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 elements (32 bytes) along K inside the swizzled row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((it - it0) | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 16 elements (32 bytes) along K inside the swizzled row: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((it - it0) | k) != 0);
+            }
+            umma_commit(empty_bar(stage));
+            if (it + 1 == it1) umma_commit(tfull_bar(acc));
           }
-          umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -542,7 +553,8 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t rfull0 = bar_base + 8u * (2 * MAX_STAGES + 4);
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4 + MAX_TEAMS * MAX_SLOTS);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // warp-uniform for ptxas
+  const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();            // CTA inside its pair: which 128 of the 256 rows
   const bool leader = rank == 0;
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
@@ -572,8 +584,8 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   if (warp == 0) {
-    // ================================================================== TMA producer (both CTAs)
-    if (lane == 0) {
+    // ================================================================== TMA producer (both CTAs; uniform loop, elected issue)
+    {
       int stage = 0, phase = 0;
       for (int work = pair_id; work < total_work; work += num_pairs) {
         const int n_tile = work % p.n_tiles;
@@ -587,29 +599,32 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int it = 0; it < k_iters; ++it) {
           const int tap = it / p.k_chunks, kc = it - tap * p.k_chunks;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t a_dst = smem_base + stage * stage_bytes;
-          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
-          if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)stage_bytes);   // bytes of BOTH CTAs
-          if (MODE == PB_A_LINEAR) {
-            tma_load_2d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
-          } else if (MODE == PB_A_CONV3X3) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx * p.cstride + kx - 1,
-                             cy * p.cstride + ky - 1, cn);
-          } else {
-            tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
+          if (elect_one()) {
+            const uint32_t a_dst = smem_base + stage * stage_bytes;
+            const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+            if (leader) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)stage_bytes);   // bytes of BOTH CTAs
+            if (MODE == PB_A_LINEAR) {
+              tma_load_2d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, m_tile * BLOCK_M);
+            } else if (MODE == PB_A_CONV3X3) {
+              const int ky = tap / 3, kx = tap - ky * 3;
+              tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx * p.cstride + kx - 1,
+                               cy * p.cstride + ky - 1, cn);
+            } else {
+              tma_load_4d_pair(a_dst, &tmA, full_bar(stage), kc * BLOCK_K, cx, cy + tap - 1, cn);
+            }
+            const int kcol = it * BLOCK_K;
+            // GEGLU: CTA 0 stages the value rows, CTA 1 the gate rows of the same output columns
+            const int wrow = GEGLU ? (int)rank * p.geglu_half + n_tile * half_n : n_tile * p.block_n + (int)rank * half_n;
+            tma_load_2d_pair(b_dst, &tmB, full_bar(stage), kcol, wrow);
           }
-          const int kcol = it * BLOCK_K;
-          // GEGLU: CTA 0 stages the value rows, CTA 1 the gate rows of the same output columns
-          const int wrow = GEGLU ? (int)rank * p.geglu_half + n_tile * half_n : n_tile * p.block_n + (int)rank * half_n;
-          tma_load_2d_pair(b_dst, &tmB, full_bar(stage), kcol, wrow);
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    if (leader) {                                      // uniform: whole warp loops, one elected lane issues
       const uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, (uint32_t)p.block_n);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int work = pair_id; work < total_work; work += num_pairs) {
@@ -619,16 +634,19 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * stage_bytes;
-          const uint64_t a_desc = make_smem_desc_sw128(a_addr);
-          const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_STAGE_BYTES);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_base + stage * stage_bytes;
+            const uint64_t a_desc = make_smem_desc_sw128(a_addr);
+            const uint64_t b_desc = make_smem_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
-          umma_commit_pair(empty_bar(stage), 3);      // both CTAs of the pair may refill this stage
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+            umma_commit_pair(empty_bar(stage), 3);      // both CTAs of the pair may refill this stage
+            if (it + 1 == k_iters) umma_commit_pair(tfull_bar(acc), 3);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(tfull_bar(acc), 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

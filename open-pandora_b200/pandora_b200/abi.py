@@ -17,8 +17,9 @@ DDIM_SQRT_AC, DDIM_SQRT_OMAC, DDIM_SQRT_A_PREV, DDIM_SIGMA, DDIM_X0_RESCALE, DDI
 DDIM_NCOEF = 8
 E_UNSUPPORTED = -3
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib",
-                         "libpandora_b200.so")
+#: PANDORA_B200_LIB selects a profiling build of the SAME library (build.py `variant`); tools only
+_LIB_PATH = os.environ.get("PANDORA_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lib", "libpandora_b200.so")
 
 
 class GemmArgs(C.Structure):

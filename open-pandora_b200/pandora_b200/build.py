@@ -32,9 +32,14 @@ def _newer(src, dst):
     return (not os.path.exists(dst)) or os.path.getmtime(src) > os.path.getmtime(dst)
 
 
-def build_library(verbose=False, force=False):
-    os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+def build_library(verbose=False, force=False, defines=(), variant=None):
+    """`variant` + `defines`: a profiling build (e.g. -DPB_ATT_TRACE) into lib/<variant>/, next to the product
+    library, selected at load time with PANDORA_B200_LIB (tools only)."""
+    libdir = LIBDIR if variant is None else os.path.join(LIBDIR, variant)
+    lib_path = os.path.join(libdir, "libpandora_b200.so")
+    flags = [*NVCC_FLAGS, *(f"-D{d}" for d in defines)]
+    os.makedirs(libdir, exist_ok=True)
+    objdir = os.path.join(libdir, "obj")
     os.makedirs(objdir, exist_ok=True)
     srcs = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
@@ -49,7 +54,7 @@ def build_library(verbose=False, force=False):
 
     def compile_one(job):
         src, obj = job
-        r = subprocess.run([nvcc, *NVCC_FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+        r = subprocess.run([nvcc, *flags, "-c", src, "-o", obj], capture_output=True, text=True)
         return src, r
 
     logs = []
@@ -59,15 +64,15 @@ def build_library(verbose=False, force=False):
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
     objs = [os.path.join(objdir, s[:-3] + ".o") for s in srcs]
-    if jobs or not os.path.exists(LIB):
-        r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcuda", "-Xcompiler", "-fPIC"],
+    if jobs or not os.path.exists(lib_path):
+        r = subprocess.run([nvcc, "-shared", "-o", lib_path, *objs, "-lcuda", "-Xcompiler", "-fPIC"],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     if verbose:
         for src, log in logs:
             print(f"== {os.path.basename(src)}\n{log}")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":

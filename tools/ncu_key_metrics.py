@@ -15,7 +15,6 @@ COLS = {
     "time_us": "gpu__time_duration.sum",
     "dram_rd": "dram__bytes_read.sum",
     "dram_wr": "dram__bytes_write.sum",
-    "tensor_pct": "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "lts_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
     "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "issue_pct": "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
@@ -62,8 +61,8 @@ def main():
     labels = json.load(open(args[1])) if len(args) > 1 else []
     rows = read(rep)
     print("| # | kernel | launch | grid x block | time us | DRAM read MB | DRAM write MB | algorithmic MB | "
-          "DRAM/alg | GB/s (alg) | TFLOP/s | tensor % | L2 % | DRAM % | issue % | warps % | regs |")
-    print("|" + "---|" * 17)
+          "DRAM/alg | GB/s (alg) | TFLOP/s | L2 % | DRAM % | issue % | warps % | regs |")
+    print("|" + "---|" * 16)
     f = lambda v, p=1: "-" if v is None else f"{v:.{p}f}"
     for i, d in enumerate(rows):
         lab = labels[i] if i < len(labels) else {}
@@ -73,7 +72,7 @@ def main():
         print(f"| {i + 1} | `{d['kernel']}` | {d['launch']} | {d['grid']} x {d['block']} | {f(d['time_us'])} | "
               f"{f(d['dram_rd'] and d['dram_rd'] / 1e6)} | {f(d['dram_wr'] and d['dram_wr'] / 1e6)} | "
               f"{f(alg and alg / 1e6)} | {f(alg and dram / alg, 2)} | {f(alg and alg / d['time_us'] / 1e3, 0)} | "
-              f"{f(fl and fl / d['time_us'] / 1e6, 0)} | {f(d['tensor_pct'])} | {f(d['lts_pct'])} | {f(d['dram_pct'])} | "
+              f"{f(fl and fl / d['time_us'] / 1e6, 0)} | {f(d['lts_pct'])} | {f(d['dram_pct'])} | "
               f"{f(d['issue_pct'])} | {f(d['warps_pct'])} | {f(d['regs'], 0)} |")
     for a in sys.argv[1:]:
         if a.startswith("--json="):
