@@ -178,7 +178,8 @@ tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t s_full = bars + 8u * (1 + 2 * X_QSTAGES), p_full = s_full + 8, o_full = s_full + 16, o_free = s_full + 24;
   const uint32_t tmem_slot = bars + 8u * X_NBARS;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // warp-uniform for ptxas
+  const int lane = threadIdx.x & 31;
   const int head = blockIdx.y, n = blockIdx.z;
   const int q_tiles = (p.nq + ATT_BM - 1) / ATT_BM;
   const int i0 = blockIdx.x * p.q_chunk;
@@ -203,47 +204,56 @@ tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // Producer and issuer loops run on the whole warp in uniform control flow with one elected lane issuing (see the
+  // note at the issuer of tc_attention3_kernel: under `if (lane == 0)` every issue sits in an election loop).
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * TILE_BYTES);       // rows past n_kv are zero-filled by the copy engine
       tma_load_3d(sK, &tmK, kv_full, head * ATT_D, 0, n / p.k_bdiv);
       tma_load_3d(sV, &tmV, kv_full, head * ATT_D, 0, n / p.v_bdiv);
-      for (int it = 0; it < nt; ++it) {
-        const int s = it % X_QSTAGES;
-        mbar_wait(q_empty(s), ((it / X_QSTAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int it = 0; it < nt; ++it) {
+      const int s = it % X_QSTAGES;
+      mbar_wait(q_empty(s), ((it / X_QSTAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(q_full(s), TILE_BYTES);
         tma_load_3d(sQ(s), &tmQ, q_full(s), head * ATT_D, (i0 + it) * ATT_BM, n / p.q_bdiv);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(ATT_BM, (uint32_t)nkv16);
-      const uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);     // B (= V) MN-major
-      const uint64_t k_desc = make_smem_desc_sw128(sK);
-      auto issue_s = [&](int it) {
-        const int s = it % X_QSTAGES;
-        mbar_wait(q_full(s), (it / X_QSTAGES) & 1);
-        tc_fence_after();
+    const uint32_t idesc_s = make_idesc_bf16(ATT_BM, (uint32_t)nkv16);
+    const uint32_t idesc_o = make_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);     // B (= V) MN-major
+    const uint64_t k_desc = make_smem_desc_sw128(sK);
+    const uint64_t v_desc = make_smem_desc_mn_sw128(sV);
+    auto issue_s = [&](int it) {
+      const int s = it % X_QSTAGES;
+      mbar_wait(q_full(s), (it / X_QSTAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t q_desc = make_smem_desc_sw128(sQ(s));
 #pragma unroll
         for (int k = 0; k < ATT_D / UMMA_K; ++k) umma_bf16(tmem_base, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
         umma_commit(s_full);
         umma_commit(q_empty(s));
-      };
-      mbar_wait(kv_full, 0);
-      issue_s(0);
-      const int ksteps = nkv16 / UMMA_K;
-      for (int it = 0; it < nt; ++it) {
-        mbar_wait(p_full, it & 1);                          // P_i is in tensor memory (S_i has been consumed)
-        if (it > 0) mbar_wait(o_free, (it - 1) & 1);        // O_i-1 has been read out
-        tc_fence_after();
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t b_desc = make_smem_desc_mn_sw128(sV + k * 16 * 128);
-          umma_bf16_ts(tmem_base + X_O_COL0, tmem_base + (uint32_t)(k * 8), b_desc, idesc_o, k != 0);
-        }
-        umma_commit(o_full);
-        if (it + 1 < nt) issue_s(it + 1);                   // executes behind PV_i: P_i is consumed before S overwrites it
       }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    issue_s(0);
+    const int ksteps = nkv16 / UMMA_K;
+    for (int it = 0; it < nt; ++it) {
+      mbar_wait(p_full, it & 1);                          // P_i is in tensor memory (S_i has been consumed)
+      if (it > 0) mbar_wait(o_free, (it - 1) & 1);        // O_i-1 has been read out
+      tc_fence_after();
+      if (elect_one()) {
+        for (int k = 0; k < ksteps; ++k)                  // 16 keys = 2048 B = 128 descriptor units
+          umma_bf16_ts(tmem_base + X_O_COL0, tmem_base + (uint32_t)(k * 8), v_desc + (uint64_t)(k * 128), idesc_o, k != 0);
+        umma_commit(o_full);
+      }
+      __syncwarp();
+      if (it + 1 < nt) issue_s(it + 1);                   // executes behind PV_i: P_i is consumed before S overwrites it
     }
   } else {
     const int quarter = warp & 3;
@@ -445,17 +455,21 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   }
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * TILE_BYTES);
       for (int t = 0; t < 2; ++t)
         tma_load_3d(sQ(t), &tmQ, q_full, head * ATT_D, (q_tile0 + t) * ATT_BM, n / p.q_bdiv);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % V3_STAGES;
-        mbar_wait(kv_empty(s), ((j / V3_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % V3_STAGES;
+      mbar_wait(kv_empty(s), ((j / V3_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(kv_full(s), 2 * TILE_BYTES);
         tma_load_3d(sK(s), &tmK, kv_full(s), head * ATT_D, j * ATT_BN, n / p.k_bdiv);
         tma_load_3d(sV(s), &tmV, kv_full(s), head * ATT_D, j * ATT_BN, n / p.v_bdiv);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // The WHOLE warp runs the event loop in uniform control flow (`warp` comes from a shuffle, so the compiler

@@ -188,6 +188,9 @@ __device__ __forceinline__ void epilogue_loop(const CUtensorMap* tmC, const CUte
   const int pf_dist = n_slots >= 3 ? 2 : 1;
   int pf_work = first, pf_ci = team;
   uint32_t pf_cnt = 0;
+  // (The leader is ONE divergent lane on purpose: run warp-uniform with an elected lane, as the producer / issuer
+  // loops are, the other 31 lanes of the leader warp wait for its bulk-group drains instead of starting the next
+  // chunk's tensor-memory loads — measured 3-5 % slower on the Linear / GEGLU family.)
   auto pf_issue = [&]() {
     if (pf_work >= total || team >= n_chunks) return;
     int nc[4], nmt, nnt;
@@ -800,14 +803,21 @@ static bool pick_brick(int W, int H, int N, int* bw, int* bh, int* bn, bool* exa
 
 static int num_sms();
 
-// Tile width: a multiple of 32 (the epilogue's chunk) dividing n_cols, <= cap.  Measured on B200 (gpurun_out
-// s10/s11 tile sweeps): the time of a k-step is nearly independent of the tile width up to 256 columns (operand
-// staging, not the tensor pipe, sets the pace), so throughput grows almost linearly with the width; a narrow tile
-// only wins when it removes a whole wave over the SMs.  cost = waves x (width + 360) in "column" units.
+// Tile width: a multiple of 32 (the epilogue's chunk) dividing n_cols, <= cap: the widest tile unless a narrower
+// one removes a whole wave over the SMs; cost = waves x (width + 360) in "column" units.  (The constant dates from
+// round 1, when an election loop around every tcgen05.mma made a k-step cost the same for every width; with the
+// uniform issuer a sweep of the constant over 48 .. 360 changes the choice on two shapes only and the total of the
+// 24 GEMM-family shapes of a forward by < 2 %: the widths that divide 320 / 640 / 1280 leave little to choose.)
 // A width that is only a multiple of 16 is legal when it is the whole output (its ragged last chunk is clipped
 // at the tensor edge by the bulk store).
 static int pick_block_n(int n_cols, int cap, int m_tiles) {
   if (n_cols <= cap && n_cols % 16 == 0 && n_cols % 32 != 0) return n_cols;
+#ifdef PB_TC_TUNING          // profiling build only: tile-width sweeps (tools/tile_sweep.py)
+  if (const char* f = getenv("PB_TC_FORCE_BN")) {
+    const int bn = atoi(f);
+    if (bn >= 32 && bn <= cap && n_cols % bn == 0) return bn;
+  }
+#endif
   int best = 0;
   long best_cost = 0;
   for (int bn = cap - cap % 32; bn >= 64 || (best == 0 && bn >= 32); bn -= 32) {

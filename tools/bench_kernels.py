@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--res", default="512")
     ap.add_argument("--what", default="gemm,geglu,conv,convt,attn,norm")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--frames", type=int, default=16,
+                    help="frames in the GEMM-family rows (16 = one clip; 32 = the batched cond|uncond forward)")
     ap.add_argument("--simt", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("--torch", action="store_true",
@@ -55,7 +57,8 @@ def main():
     g = torch.Generator(device=dev).manual_seed(0)
     rn = lambda *s: torch.randn(*s, device=dev, generator=g).to(BF)
     what = a.what.split(",")
-    lv = [(16 * H * W, 320), (16 * H * W // 4, 640), (16 * H * W // 16, 1280), (16 * H * W // 64, 1280)]
+    FR = a.frames
+    lv = [(FR * H * W, 320), (FR * H * W // 4, 640), (FR * H * W // 16, 1280), (FR * H * W // 64, 1280)]
     if "gemm" in what:
         for (M, C) in lv[:3]:
             for (N, K, role) in [(C, C, "proj"), (3 * C, C, "qkv"), (C, 4 * C, "ff_out")]:
@@ -71,14 +74,14 @@ def main():
         for i, (cin, cout) in enumerate([(320, 320), (640, 640), (1280, 1280), (1280, 1280)]):
             h, w_ = H >> i, W >> i
             for ci in (cin, 2 * cin):
-                M = 16 * h * w_
+                M = FR * h * w_
                 x, w, c = rn(M, ci), rn(cout, 9 * ci), torch.empty(M, cout, device=dev)
                 t = timeit(lambda: abi.gemm(x, w, c, mode=abi.A_CONV3X3, conv=(ci, h, w_, h, w_, 1, 0), tc=tc), a.reps, flush)
                 rows.append(dict(kind="conv3x3", cin=ci, cout=cout, H=h, W=w_, ms=t * 1e3, tflops=2 * M * cout * 9 * ci / t / 1e12))
     if "convt" in what:
         for i, C in enumerate([320, 640, 1280, 1280]):
             hw = (H >> i) * (W >> i)
-            M = 16 * hw
+            M = FR * hw
             x, w, c = rn(M, C), rn(C, 3 * C), torch.empty(M, C, device=dev)
             t = timeit(lambda: abi.gemm(x, w, c, mode=abi.A_CONVT3, convt=(C, 16, hw), tc=tc), a.reps, flush)
             rows.append(dict(kind="convt3", C=C, HW=hw, ms=t * 1e3, tflops=2 * M * C * 3 * C / t / 1e12))
