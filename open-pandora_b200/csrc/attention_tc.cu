@@ -132,6 +132,38 @@ __device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
       : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
 }
 
+// 2^e for a PAIR of scores on the FMA pipe (no MUFU): e = n + f with n = round(e), f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the bf16 rounding of P), and n goes
+// straight into the exponent field.  Packed f32x2 adds / FMAs: 10 issue slots per pair against 2 MUFU.EX2 that
+// occupy the 4-lane MUFU pipe for 16 cycles.  Used for a fixed fraction of the pairs so that both pipes are busy.
+__device__ __forceinline__ void exp2_poly2(float e0, float e1, float& p0, float& p1) {
+  e0 = fmaxf(e0, -126.0f);
+  e1 = fmaxf(e1, -126.0f);
+  float r0, r1, q0, q1;
+  asm("{\n.reg .b64 a, m, nm, r, n, f, q, c;\n"
+      "mov.b64 a, {%4, %5};\n"
+      "mov.b64 m, {%6, %6};\n"
+      "mov.b64 nm, {%7, %7};\n"
+      "add.rn.f32x2 r, a, m;\n"          // low mantissa bits = round(e) (two's complement)
+      "add.rn.f32x2 n, r, nm;\n"         // n = round(e) as a float
+      "mov.b64 c, {%8, %8};\n"
+      "fma.rn.f32x2 f, n, c, a;\n"       // f = e - n
+      "mov.b64 q, {%9, %9};\n"
+      "mov.b64 c, {%10, %10};\n"
+      "fma.rn.f32x2 q, q, f, c;\n"
+      "mov.b64 c, {%11, %11};\n"
+      "fma.rn.f32x2 q, q, f, c;\n"
+      "mov.b64 c, {%12, %12};\n"
+      "fma.rn.f32x2 q, q, f, c;\n"
+      "mov.b64 {%0, %1}, r;\n"
+      "mov.b64 {%2, %3}, q;\n}"
+      : "=f"(r0), "=f"(r1), "=f"(q0), "=f"(q1)
+      : "f"(e0), "f"(e1), "f"(12582912.0f), "f"(-12582912.0f), "f"(-1.0f), "f"(0.055171672f), "f"(0.24261114f),
+        "f"(0.69326097f), "f"(0.99992806f));
+  p0 = __int_as_float((__float_as_int(r0) << 23) + __float_as_int(q0));
+  p1 = __int_as_float((__float_as_int(r1) << 23) + __float_as_int(q1));
+}
+
 // ================================================================================================
 // Single key tile (n_kv <= 128): text + image cross-attention (93 keys per frame, two softmax segments), and the
 // self-attention of the smallest levels.  The work is HBM-shaped (a 128-query tile reads 16 KiB of Q and writes
@@ -396,6 +428,11 @@ tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 //     2^8, exact in fp32 and harmless in bf16 — so there is no per-tile fold of O.
 //   * the issuer is an event loop: it polls s_free / p_full of both query tiles and issues whichever product has its
 //     operands ready, so the two query tiles drift into whatever phase keeps the MUFU and the tensor pipe busiest.
+//     The whole warp runs that loop in uniform control flow with one elected lane issuing (see the note there).
+//   * one eighth of the exponentials is evaluated on the FMA pipe (exp2_poly2) to take load off the MUFU.
+// Measured alternatives that were NOT better (tools/attn_timeline.py, same box): strict ping-pong of the two
+// tiles' exponential phases through named barriers (each phase alone keeps the MUFU only 70 % busy: -3 %), one
+// straight-line issuer warp per tile instead of the polling loop (-5 %), 2/8 .. 4/8 polynomial share (0 .. -10 %).
 // TMEM columns: S_0 [0,128) S_1 [128,256) P_0 [256,320) P_1 [320,384) O_0 [384,448) O_1 [448,512).
 // (Measured on the version this replaces, where S_t,j+1 could only be issued after PV_t,j because P aliased S:
 // 39 % of the softmax warps' samples were spent waiting for the next score tile, tensor pipe 26 % active.)
@@ -403,6 +440,7 @@ constexpr int V3_STAGES = 4;
 constexpr int V3_SMEM = TILE_BYTES * (2 + 2 * V3_STAGES);      // Q x2 + (K, V) x4 = 160 KiB
 constexpr float V3_RESCALE_THRESHOLD = 8.0f;                    // log2 units
 constexpr int V3_P_COL0 = 256, V3_O_COL0 = 384;
+constexpr int V3_POLY_EIGHTHS = 1;      // eighths of the exponentials evaluated on the FMA pipe (exp2_poly2)
 constexpr int V3_NBARS = 1 + 2 * V3_STAGES + 8;                 // q_full, kv_full/empty, {s_full, s_free, p_full, o_full} x 2
 
 // 384 threads = three warpgroups: {TMA producer, MMA issuer, two idle warps} | softmax of query tile 0 | softmax of
@@ -611,7 +649,9 @@ tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int i = 0; i < 32; i += 2) {
             float e0, e1;
             fma2(e0, e1, v[c][i], v[c][i + 1], p.scale_log2, neg_m);
-            const float p0 = fast_exp2(e0), p1 = fast_exp2(e1);
+            float p0, p1;
+            if (((c * 16 + (i >> 1)) & 7) < V3_POLY_EIGHTHS) exp2_poly2(e0, e1, p0, p1);
+            else { p0 = fast_exp2(e0); p1 = fast_exp2(e1); }
             add2(lq[(i & 2)], lq[(i & 2) + 1], p0, p1);
             w[c][i >> 1] = pack_bf16_alu(p0, p1);
           }
