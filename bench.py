@@ -443,12 +443,12 @@ def main():
         fam = [a for k, a in agg.items() if k.startswith("tc_gemm") or k.startswith("tc_conv")]
         # DRAM traffic of the family's most expensive launch shape, from the committed `ncu --set full` capture
         traffic = traffic_note = None
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if args.res == "512" and os.path.exists(tpath):
             t0 = json.load(open(tpath))["launches"][0]
             traffic = t0["dram_bytes"]
             traffic_note = dict(launch=t0["launch"], dram_bytes=t0["dram_bytes"], algorithmic_bytes=t0["algorithmic_bytes"],
-                                source="profiles/r1_ncu_full_key_metrics.md row 1 (ncu --set full, per launch)")
+                                source="profiles/r2_ncu_full_key_metrics.md row 1 (ncu --set full, per launch)")
         if fam:
             fl, ms, n = sum(a["flops"] for a in fam), sum(a["ms"] for a in fam), sum(a["n"] for a in fam)
             ach = fl / ms / 1e9
