@@ -65,6 +65,14 @@ def _worker(rank, world, port, mode, ret):
                             verbose=False, timestep_spacing="uniform_trailing", guidance_rescale=0.7)
             ret[rank] = x.float().cpu()
     finally:
+        # captured graphs holding NCCL kernels make destroy_process_group() block for a long time: drop them first
+        import gc
+        try:
+            m._graph_cache.clear()
+        except NameError:
+            pass
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
