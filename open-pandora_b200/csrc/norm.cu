@@ -82,8 +82,10 @@ layernorm_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y, int6
 }
 
 // ---- exact-fit variant: cv == L * NV
-template <typename TX, typename TY, int L, int NV, bool HOIST>
-__global__ void __launch_bounds__(256)
+// PF = false: one row group per warp and no prefetch buffer (short inputs: C = 1280 at the deep levels is 5120 rows =
+// 640 CTAs; without the second row buffer the kernel fits two CTAs per SM, i.e. half as many waves of load latency).
+template <typename TX, typename TY, int L, int NV, bool HOIST, bool PF = true>
+__global__ void __launch_bounds__(256, PF ? 1 : 2)
 layernorm_rows_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y, int64_t ldy, int64_t rows,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
   constexpr int RPW = 32 / L;                       // rows per warp pass
@@ -98,7 +100,7 @@ layernorm_rows_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y,
 #pragma unroll
     for (int i = 0; i < NV; ++i) { load4(gamma + (sl + L * i) * 4, gh[HOIST ? i : 0]); load4(beta + (sl + L * i) * 4, bh[HOIST ? i : 0]); }
   }
-  float cur[NV][4], nxt[NV][4];
+  float cur[NV][4], nxt[PF ? NV : 1][4];
   auto load_row = [&](int64_t g, float (&dst)[NV][4]) {
     int64_t row = g * RPW + sub;
     if (row >= rows) row = rows - 1;                // tail: load a valid row, the store is skipped
@@ -109,7 +111,9 @@ layernorm_rows_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y,
   if (warp0 < groups) load_row(warp0, cur);
   for (int64_t g = warp0; g < groups; g += nwarps) {
     const bool more = g + nwarps < groups;
-    if (more) load_row(g + nwarps, nxt);
+    if constexpr (PF) {
+      if (more) load_row(g + nwarps, nxt);
+    }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) s += (cur[i][0] + cur[i][1]) + (cur[i][2] + cur[i][3]);
@@ -144,12 +148,16 @@ layernorm_rows_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y,
         store4(yr + (sl + L * i) * 4, o);
       }
     }
-    if (more) {
+    if constexpr (PF) {
+      if (more) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
+        for (int i = 0; i < NV; ++i) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cur[i][j] = nxt[i][j];
+          for (int j = 0; j < 4; ++j) cur[i][j] = nxt[i][j];
+        }
       }
+    } else {
+      break;                                        // launched with one row group per warp
     }
   }
 }
@@ -241,11 +249,16 @@ int pb_layernorm(const void* x, int32_t x_dtype, int64_t ldx, void* y, int32_t y
 #define PB_LN_ROWS(L_, NV_, H_)                                                                                   \
     do {                                                                                                           \
       const int64_t groups = ceil_div(rows, 32 / (L_));                                                            \
-      if (fb > ceil_div(groups, 8)) fb = ceil_div(groups, 8);                                                      \
+      const bool single = ceil_div(groups, 8) <= fb;       /* one row group per warp: no prefetch buffer */         \
+      if (single) fb = ceil_div(groups, 8);                                                                        \
       PB_DISPATCH_DTYPE(x_dtype, TX, {                                                                             \
         PB_DISPATCH_DTYPE(y_dtype, TY, {                                                                           \
-          layernorm_rows_kernel<TX, TY, L_, NV_, H_><<<(unsigned)fb, 256, 0, st>>>(                                \
-              reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<TY*>(y), ldy, rows, gamma, beta, eps);         \
+          if (single && (NV_) >= 10)                                                                               \
+            layernorm_rows_kernel<TX, TY, L_, NV_, H_, false><<<(unsigned)fb, 256, 0, st>>>(                       \
+                reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<TY*>(y), ldy, rows, gamma, beta, eps);       \
+          else                                                                                                     \
+            layernorm_rows_kernel<TX, TY, L_, NV_, H_><<<(unsigned)fb, 256, 0, st>>>(                              \
+                reinterpret_cast<const TX*>(x), ldx, reinterpret_cast<TY*>(y), ldy, rows, gamma, beta, eps);       \
         })                                                                                                         \
       })                                                                                                           \
       PB_LAUNCH_CHECK("layernorm_rows_kernel");                                                                    \
