@@ -214,13 +214,24 @@ gn_cols_partial_kernel(const float* __restrict__ cs, int64_t ld_cs, int C, int G
   const int64_t slabs = R >> 5;
   const int64_t s0 = slabs * sp / splits, s1 = slabs * (sp + 1) / splits;
   const float* base = cs + ((int64_t)inst * slabs + s0) * ld_cs + 2 * (int64_t)g * cpg;
-  const int64_t total = (s1 - s0) * cpg;
+  const int total = (int)(s1 - s0) * cpg;          // < 2^31: slabs of one instance x channels of one group
   double s = 0.0, q = 0.0;
-  for (int64_t i = threadIdx.x; i < total; i += 256) {
-    const int64_t sl = i / cpg;
-    const int c = (int)(i - sl * cpg);
-    const float2 v = *reinterpret_cast<const float2*>(base + sl * ld_cs + 2 * c);
-    s += (double)v.x; q += (double)v.y;
+  // 32-bit indexing and four independent loads in flight per thread: the kernel moves a few MB and is pure latency
+  // (the first version did a 64-bit division per element and had one load outstanding)
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * 256) {
+    float2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i < total) {
+        const int sl = i / cpg, c = i - sl * cpg;
+        v[u] = *reinterpret_cast<const float2*>(base + (int64_t)sl * ld_cs + 2 * c);
+      } else {
+        v[u] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { s += (double)v[u].x; q += (double)v[u].y; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
