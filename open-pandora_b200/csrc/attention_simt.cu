@@ -35,6 +35,7 @@ __device__ __forceinline__ int64_t batch_off(int64_t n, int64_t bdiv, int64_t bs
 
 template <typename T>
 __global__ void __launch_bounds__(128) attn_simt_kernel(AttnP p) {
+  pb::pdl_trigger();
   __shared__ __align__(16) float Ks[KT][AD];
   __shared__ __align__(16) float Vs[KT][AD];
   const int64_t n = blockIdx.x / p.qtiles;

@@ -198,6 +198,7 @@ template <int NCH, int CSP, int CNK>
 __global__ void __launch_bounds__(192, NCH == 3 ? 2 : 1)
 tc_attention_x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, const AttP p) {
+  pb::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base, sV = base + TILE_BYTES;
@@ -449,6 +450,7 @@ constexpr int V3_NBARS = 1 + 2 * V3_STAGES + 8;                 // q_full, kv_fu
 __global__ void __launch_bounds__(384, 1)
 tc_attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const AttP p) {
+  pb::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   auto sQ = [&](int t) { return base + TILE_BYTES * t; };

@@ -32,6 +32,7 @@ struct SmallAttnP {
 
 template <typename T>
 __global__ void __launch_bounds__(32 * T_WARPS) attn_small_kernel(SmallAttnP p) {
+  pb::pdl_trigger();
   __shared__ __align__(16) float Ks[T_WARPS][TS_MAX][TD];
   __shared__ __align__(16) float Vs[T_WARPS][TS_MAX][TD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -149,6 +150,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 __global__ void __launch_bounds__(32 * TM_WARPS) attn_small_mma_kernel(SmallAttnP p) {
+  pb::pdl_trigger();
   // per warp: Q, K, V tiles [16 rows][64 bf16] = 128 B rows, 16-byte chunk c of row j stored at chunk c ^ (j & 7)
   __shared__ __align__(128) uint8_t tiles[TM_WARPS][3][TS_MAX * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

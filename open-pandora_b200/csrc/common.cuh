@@ -9,6 +9,23 @@
 
 namespace pb {
 
+// Programmatic dependent launch (-DPB_PDL).  Every kernel lets its dependents start launching as soon as all of its own
+// CTAs are resident (`pdl_trigger` first thing); the tcgen05 GEMM kernels are launched with the programmatic-serialisation
+// attribute and call `pdl_wait` AFTER their prologue (barrier init, tensor-memory allocation, tensor-map prefetch) and
+// before they touch global memory, so that prologue runs under the predecessor's tail.  `griddepcontrol.wait` returns
+// when the prerequisite grids have completed and their memory is visible: results cannot depend on the overlap.
+__device__ __forceinline__ void pdl_trigger() {
+#ifdef PB_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifdef PB_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+
 // thread-local last-error text (pb_last_error)
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

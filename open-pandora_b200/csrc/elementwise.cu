@@ -17,6 +17,7 @@ static inline unsigned grid_for(int64_t n, int threads = 256, int64_t cap = 148 
 template <typename TU, typename TY>
 __global__ void geglu_kernel(const TU* __restrict__ u, int64_t ldu, TY* __restrict__ y, int64_t ldy,
                              int64_t n_out, int64_t total_vec) {
+  pb::pdl_trigger();
   const int64_t cv = n_out >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -31,6 +32,7 @@ __global__ void geglu_kernel(const TU* __restrict__ u, int64_t ldu, TY* __restri
 }
 
 __global__ void silu_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pb::pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     y[i] = v / (1.0f + expf(-v));
@@ -38,6 +40,7 @@ __global__ void silu_kernel(const float* __restrict__ x, float* __restrict__ y, 
 }
 
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, int64_t n) {
+  pb::pdl_trigger();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = a[i] + b[i];
 }
@@ -45,6 +48,7 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
 template <typename TS, typename TD>
 __global__ void copy_rows_kernel(const TS* __restrict__ s, int64_t lds, TD* __restrict__ d, int64_t ldd,
                                  int64_t cols, int64_t total_vec) {
+  pb::pdl_trigger();
   const int64_t cv = cols >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -59,6 +63,7 @@ __global__ void copy_rows_kernel(const TS* __restrict__ s, int64_t lds, TD* __re
 template <typename TS, typename TD>
 __global__ void upsample2x_kernel(const TS* __restrict__ s, int64_t lds, TD* __restrict__ d, int64_t ldd,
                                   int H, int W, int64_t cols, int64_t total_vec) {
+  pb::pdl_trigger();
   const int64_t cv = cols >> 2;
   const int W2 = 2 * W, H2 = 2 * H;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
@@ -78,6 +83,7 @@ __global__ void upsample2x_kernel(const TS* __restrict__ s, int64_t lds, TD* __r
 // out[b, j] = cos(t_b * f_j), out[b, half + j] = sin(t_b * f_j); precise cosf/sinf (arguments reach ~1e3)
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
                                           float* __restrict__ out, int64_t batch, int64_t half) {
+  pb::pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * half) return;
   const int64_t b = i / half, j = i - b * half;
@@ -90,6 +96,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const f
 template <typename T>
 __global__ void video_to_rows_kernel(const T* __restrict__ x1, int c1, const T* __restrict__ x2, int c2,
                                      float* __restrict__ rows, int64_t ld, int64_t b, int64_t t, int64_t hw) {
+  pb::pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over (b, t, p)
   if (i >= b * t * hw) return;
   const int64_t p = i % hw, bt = i / hw, tt = bt % t, bb = bt / t;
@@ -101,6 +108,7 @@ __global__ void video_to_rows_kernel(const T* __restrict__ x1, int c1, const T* 
 template <typename T>
 __global__ void rows_to_video_kernel(const float* __restrict__ rows, int64_t ld, T* __restrict__ out,
                                      int64_t b, int c, int64_t t, int64_t hw) {
+  pb::pdl_trigger();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b * t * hw) return;
   const int64_t p = i % hw, bt = i / hw, tt = bt % t, bb = bt / t;
@@ -111,6 +119,7 @@ __global__ void rows_to_video_kernel(const float* __restrict__ rows, int64_t ld,
 // --------------------------------------------------------------------------------- CFG + DDIM step
 // ws layout (double): [batch][4] = sum(v_cond), sumsq(v_cond), sum(v_cfg), sumsq(v_cfg)
 __global__ void ddim_zero_ws_kernel(double* ws, int n) {
+  pb::pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ws[i] = 0.0;
 }
@@ -128,6 +137,7 @@ __device__ __forceinline__ float guided3(float c, float u, float ui, float s, fl
 __global__ void __launch_bounds__(256)
 ddim_stats_kernel(const float* __restrict__ vc, const float* __restrict__ vu, const float* __restrict__ vi,
                   int64_t n, float s, float s_img, double* __restrict__ ws) {
+  pb::pdl_trigger();
   const int b = blockIdx.y;
   const float* c = vc + (int64_t)b * n;
   const float* u = vu + (int64_t)b * n;
@@ -166,6 +176,7 @@ ddim_update_kernel(const float* x /* may alias xp: in-place update of the graph'
                    const float* __restrict__ noise, float* xp, float* __restrict__ x0o,
                    int64_t n, float s, float s_img, float phi, float temperature, const float* __restrict__ tables,
                    const int32_t* __restrict__ step_index, const double* __restrict__ ws) {
+  pb::pdl_trigger();
   const int b = blockIdx.y;
   const float* tb = tables + (int64_t)(*step_index) * PB_DDIM_NCOEF;
   const float sa = tb[PB_DDIM_SQRT_AC], so = tb[PB_DDIM_SQRT_OMAC], sap = tb[PB_DDIM_SQRT_A_PREV];

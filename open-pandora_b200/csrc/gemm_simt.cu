@@ -84,6 +84,7 @@ __device__ __forceinline__ int64_t a_offset(const GemmP& p, const RowInfo& r, in
 
 template <typename TA, typename TC, int MODE>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmP p) {
+  pb::pdl_trigger();
   __shared__ float As[BK][BM + PAD];
   __shared__ float Bs[BK][BN + PAD];
   const int tid = threadIdx.x;
@@ -219,6 +220,7 @@ constexpr int GEMV_MAX_M = 8;
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ w, const float* __restrict__ bias,
                  float* __restrict__ c, int64_t ldc, int M, int N, int K) {
+  pb::pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + warp;
   if (n >= N) return;

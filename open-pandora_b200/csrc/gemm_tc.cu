@@ -383,6 +383,7 @@ template <int MODE, bool GEGLU, typename TC>
 __global__ void __launch_bounds__(num_threads(GEGLU), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  pb::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // manual 1024-byte alignment (swizzle-128B atoms)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -422,6 +423,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();               // everything above ran under the predecessor's tail; global memory is touched from here on
 
   if (warp == 0) {
     // ================================================================== TMA producer (uniform loop, elected issue)
@@ -569,6 +571,7 @@ template <int MODE, bool GEGLU, typename TC>
 __global__ void __launch_bounds__(num_threads(GEGLU), 1)      // cluster of 2 CTAs (launch attribute)
 tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
+  pb::pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int half_n = p.block_n >> 1;                        // W rows staged by this CTA
@@ -611,6 +614,7 @@ tc_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();               // everything above ran under the predecessor's tail; global memory is touched from here on
 
   if (warp == 0) {
     // ================================================================== TMA producer (both CTAs; uniform loop, elected issue)
@@ -697,6 +701,7 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int N, TC* __restrict__ c, int64_t ldc,
                      const float* __restrict__ bias, const float* __restrict__ rowbias, int64_t ldrb, int64_t rb_rows,
                      const float* __restrict__ residual, int64_t ldr) {
+  pb::pdl_trigger();
   const int64_t nv = N >> 2, total = M * nv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / nv;
@@ -887,7 +892,19 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   int grid = p.m_tiles * p.n_tiles * p.splits;
   if (grid > num_sms()) grid = num_sms();
+#ifdef PB_PDL
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(num_threads(GEGLU)); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, p);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(tc_gemm_kernel)");
+#else
   kern<<<grid, num_threads(GEGLU), smem, st>>>(tmA, tmB, tmC, tmR, p);
+#endif
   PB_LAUNCH_CHECK("tc_gemm_kernel");
   return PB_OK;
 }
@@ -905,10 +922,15 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.blockDim = dim3(num_threads(GEGLU)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+#ifdef PB_PDL
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = 2;
+#endif
   if (max_clusters == 0) {
     cfg.gridDim = dim3((unsigned)(num_sms() / 2 * 2));
     int n = 0;

@@ -50,6 +50,7 @@ template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_partial_kernel(const T* __restrict__ x, int64_t ldx, int64_t R, int C, int G, int splits, int TX, int TY,
                   float* __restrict__ ws /* [n_inst, splits, G, 2] */) {
+  pb::pdl_trigger();
   __shared__ float red[GN_THREADS * 8];
   __shared__ float chan[GN_MAX_C * 2];           // per-channel (sum, sumsq) of this CTA's rows
   const int inst = blockIdx.y, sp = blockIdx.x;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(128)
 gn_finalize_kernel(const float* __restrict__ ws, int splits, int C, int G, int64_t R, float eps,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ scale_shift /* [n_inst, 2, C] */) {
+  pb::pdl_trigger();
   __shared__ double red[2][4];
   __shared__ float stat[2];
   const int inst = blockIdx.x / G, g = blockIdx.x % G;
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(256)
 gn_finalize_cols_kernel(const float* __restrict__ cs, int64_t ld_cs, int C, int G, int64_t R, float eps,
                         const float* __restrict__ gamma, const float* __restrict__ beta,
                         float* __restrict__ scale_shift /* [n_inst, 2, C] */) {
+  pb::pdl_trigger();
   __shared__ double red[2][8];
   __shared__ float stat[2];
   const int inst = blockIdx.x / G, g = blockIdx.x % G;
@@ -208,6 +211,7 @@ gn_finalize_cols_kernel(const float* __restrict__ cs, int64_t ld_cs, int C, int 
 __global__ void __launch_bounds__(256)
 gn_cols_partial_kernel(const float* __restrict__ cs, int64_t ld_cs, int C, int G, int64_t R, int splits,
                        double* __restrict__ ws) {
+  pb::pdl_trigger();
   __shared__ double red[2][8];
   const int inst = blockIdx.x / G, g = blockIdx.x % G, sp = blockIdx.y;
   const int cpg = C / G;
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(128)
 gn_finalize_f64_kernel(const double* __restrict__ ws, int splits, int C, int G, int64_t R, float eps,
                        const float* __restrict__ gamma, const float* __restrict__ beta,
                        float* __restrict__ scale_shift) {
+  pb::pdl_trigger();
   __shared__ float stat[2];
   const int inst = blockIdx.x / G, g = blockIdx.x % G;
   const int cpg = C / G;
@@ -281,6 +286,7 @@ gn_finalize_f64_kernel(const double* __restrict__ ws, int splits, int C, int G, 
 // all-reduced across ranks by the caller, then turned into the per-channel affine with the GLOBAL count.
 __global__ void __launch_bounds__(128)
 gn_sums_kernel(const float* __restrict__ ws, int splits, int G, double* __restrict__ sums /* [n_inst, G, 2] */) {
+  pb::pdl_trigger();
   __shared__ double red[2][4];
   const int inst = blockIdx.x / G, g = blockIdx.x % G;
   const float* base = ws + ((int64_t)inst * splits * G + g) * 2;
@@ -306,6 +312,7 @@ gn_sums_kernel(const float* __restrict__ ws, int splits, int G, double* __restri
 __global__ void gn_affine_kernel(const double* __restrict__ sums, int C, int G, double count, float eps,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float* __restrict__ scale_shift, int total /* n_inst * C */) {
+  pb::pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int inst = i / C, c = i - inst * C, g = c / (C / G);
@@ -376,6 +383,7 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int64_t R, int C,
                 const float* __restrict__ scale_shift, int silu, int rows_per_cta, GnFold fold,
                 TY_* __restrict__ xc /* optional: plain copy of x in y's dtype, row pitch ldc */, int64_t ldc) {
+  pb::pdl_trigger();
   extern __shared__ float4 gn_ab[];               // [cv] scale vectors, then [cv] shift vectors
   __shared__ float g_mean[32], g_rstd[32];
   const int inst = blockIdx.y;
@@ -497,6 +505,7 @@ template <typename TX_, typename TY_, int CS>       // CS = CTAs per (instance, 
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(GN_THREADS)
 gn_group_kernel(const TX_* __restrict__ x, int64_t ldx, TY_* __restrict__ y, int64_t ldy, int R, int C, int G, float eps,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu) {
+  pb::pdl_trigger();
   __shared__ double red[2][GN_THREADS / 32];
   __shared__ double part[2];
   __shared__ float stat[2];

@@ -22,6 +22,7 @@ template <typename TX, typename TY, int NV, bool PREFETCH>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y, int64_t ldy, int64_t rows,
                  int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  pb::pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -88,6 +89,7 @@ template <typename TX, typename TY, int L, int NV, bool HOIST, bool PF = true>
 __global__ void __launch_bounds__(256, PF ? 1 : 2)
 layernorm_rows_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y, int64_t ldy, int64_t rows,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  pb::pdl_trigger();
   constexpr int RPW = 32 / L;                       // rows per warp pass
   constexpr float INV_C = 1.0f / (float)(4 * L * NV);
   const int lane = threadIdx.x & 31;
@@ -168,6 +170,7 @@ layernorm_rows_kernel(const TX* __restrict__ x, int64_t ldx, TY* __restrict__ y,
 template <typename TY>
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const float* __restrict__ x, int64_t ldx, TY* __restrict__ y, int64_t ldy, int n, float scale_log2) {
+  pb::pdl_trigger();
   __shared__ float red_m[8], red_l[8];
   const float* xr = x + (int64_t)blockIdx.x * ldx;
   TY* yr = y + (int64_t)blockIdx.x * ldy;

@@ -103,6 +103,7 @@ constexpr int RS_UNROLL = 4;
 
 __global__ void __launch_bounds__(RS_THREADS)
 sp_reshard_kernel(const ReshardP p) {
+  pb::pdl_trigger();
   const uint32_t e = sp_barrier_enter(p.bar);
   const int P = p.bar.P, rank = p.bar.rank;
   const int T = P * p.t_local;
@@ -156,6 +157,7 @@ struct GnPeersP {
 
 __global__ void __launch_bounds__(256)
 sp_gn_affine_kernel(const GnPeersP p) {
+  pb::pdl_trigger();
   __shared__ float s_mean[64], s_rstd[64];
   const uint32_t e = sp_barrier_enter(p.bar);
   const int ng = p.n_inst * p.G;

@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
+    "-DPB_PDL",        # programmatic dependent launch of the tcgen05 GEMM kernels (csrc/common.cuh)
 ]
 
 
