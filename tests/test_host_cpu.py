@@ -158,6 +158,8 @@ obj = instantiate_from_config({"target": "lvdm.modules.networks.openaimodel3d.UN
 assert type(obj) is pandora_b200.UNetModel
 ddim_mod = __import__("lvdm.models.samplers.ddim", fromlist=["DDIMSampler"])
 assert ddim_mod.DDIMSampler is pandora_b200.DDIMSampler
+ddim3_mod = __import__("lvdm.models.samplers.ddim_multiplecond", fromlist=["DDIMSampler"])
+assert ddim3_mod.DDIMSampler is pandora_b200.DDIMSampler_multicond        # the class model.py:449 imports
 print("DROP_IN_OK")
 ''' % (REF_DC, os.path.join(ROOT, "open-pandora_b200"), ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
@@ -192,3 +194,30 @@ def test_vae_parameter_tree_matches_the_oracle_inventory_and_the_reference():
     m.load_state_dict(ref_sd, strict=True)
     shared = AutoencoderKL.from_reference(ref, config.VAE_DDCONFIG)
     assert shared.decoder.conv_in.weight is ref.decoder.conv_in.weight
+
+
+def test_multicond_sampler_host_logic():
+    """Three-branch sampler (ddim_multiplecond.py): the third conditioning is a REQUIRED kwarg (KeyError like the
+    reference's `kwargs['unconditional_conditioning_img_nonetext']`, :226), `cfg_img` defaults to the text scale
+    (:222-223), the schedule is the two-branch sampler's fp32 one, and a captured step is keyed by the extra branch."""
+    import numpy as np
+    import torch
+    from pandora_b200 import DDIMSampler, DDIMSampler_multicond, LatentDiffusionLite, UNetModel, config
+    from pandora_b200.sampler import GraphedCFGStep
+    model = LatentDiffusionLite(UNetModel(**config.small_unet()), **config.DIFFUSION_512)
+    s3, s2 = DDIMSampler_multicond(model), DDIMSampler(model)
+    with pytest.raises(KeyError):
+        s3._third_branch({}, 7.5)
+    uc_img = dict(c_crossattn=[torch.zeros(1, 93, 8)], c_concat=[torch.zeros(1, 4, 16, 8, 8)])
+    assert s3._third_branch(dict(unconditional_conditioning_img_nonetext=uc_img), 7.5) == (uc_img, 7.5)
+    assert s3._third_branch(dict(unconditional_conditioning_img_nonetext=uc_img, cfg_img=2.0), 7.5) == (uc_img, 2.0)
+    assert s2._third_branch(dict(unconditional_conditioning_img_nonetext=uc_img, cfg_img=2.0), 7.5) == (None, 0.0)
+    for s in (s2, s3):
+        s.make_schedule(8, "uniform_trailing", 1.0, verbose=False)
+    assert np.array_equal(s2.ddim_timesteps, s3.ddim_timesteps)
+    assert torch.equal(torch.as_tensor(s2.ddim_sigmas), torch.as_tensor(s3.ddim_sigmas))
+    assert s3.ddim_sigmas.dtype == torch.float64 and s3.alphas_cumprod.dtype == torch.float32
+    # branch bookkeeping of the captured step: [(context, c_concat)] per branch in cond, uncond, image-only order
+    cond = dict(c_crossattn=[torch.ones(1, 93, 8)], c_concat=[torch.ones(1, 4, 16, 8, 8)])
+    srcs = GraphedCFGStep._sources(cond, cond, uc_img)
+    assert len(srcs) == 3 and srcs[2][0] is uc_img["c_crossattn"][0] and len(GraphedCFGStep._sources(cond, None)) == 1
